@@ -1,0 +1,599 @@
+// bfe2.cu -- kernels + C ABI of libbfe2.so (see include/bfe2.h).  sm_100a only, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bfe2.h"
+#include "bfe2_device.cuh"
+
+using namespace bfe2;
+
+// =================================================================================================
+// error plumbing
+// =================================================================================================
+namespace {
+thread_local std::string g_err = "";
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define BFE2_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) return fail(-100, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+}  // namespace
+
+// =================================================================================================
+// topology plan (host)
+// =================================================================================================
+struct bfe2_plan {
+    int nN = 0, nE = 0, sumdof = 0, n = 0, hbw = 0, nslots = 0, ncontrib = 0;
+    int npad = 0, LD = 0, rpl = 0, lpp = 0, nthreads = 0;
+    std::vector<int32_t> conn, free_of_pos, pos_of_free, fixed, slot_ptr, contrib, node_ptr, node_inc;
+    std::vector<uint8_t> lumped;
+    // device mirror (uploaded lazily on the first launch, on the then-current device)
+    bool uploaded = false;
+    int device = -1;
+    void* d_blob = nullptr;
+    PlanDev dev{};
+};
+
+namespace {
+
+// Jacobi lane configuration for n free DOFs: RPL rows per lane, LPP lanes per column pair.
+bool jacobi_config(int n, int* rpl, int* lpp) {
+    if (n <= 10) { *rpl = 5; *lpp = 2; return true; }
+    if (n <= 30) { *rpl = 15; *lpp = 2; return true; }
+    if (n <= 58) { *rpl = 29; *lpp = 2; return true; }
+    if (n <= 116 && n <= BFE2_MAX_JACOBI_N) { *rpl = 29; *lpp = 4; return true; }
+    return false;
+}
+
+int plan_upload(bfe2_plan* p) {
+    int dev = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    if (p->uploaded && p->device == dev) return 0;
+    if (p->uploaded) { cudaFree(p->d_blob); p->uploaded = false; p->d_blob = nullptr; }
+    // one blob: all int32 arrays then the uint8 flags
+    const std::vector<int32_t>* arrs[7] = {&p->conn, &p->free_of_pos, &p->pos_of_free, &p->slot_ptr,
+                                           &p->contrib, &p->node_ptr, &p->node_inc};
+    size_t off[8];
+    size_t tot = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = tot; tot += ((arrs[i]->size() + 3) & ~size_t(3)); }
+    off[7] = tot;
+    const size_t bytes = tot * sizeof(int32_t) + ((p->lumped.size() + 15) & ~size_t(15));
+    std::vector<unsigned char> host(bytes, 0);
+    for (int i = 0; i < 7; ++i)
+        if (!arrs[i]->empty()) memcpy(host.data() + off[i] * 4, arrs[i]->data(), arrs[i]->size() * 4);
+    if (!p->lumped.empty()) memcpy(host.data() + off[7] * 4, p->lumped.data(), p->lumped.size());
+    BFE2_CUDA(cudaMalloc(&p->d_blob, bytes));
+    BFE2_CUDA(cudaMemcpy(p->d_blob, host.data(), bytes, cudaMemcpyHostToDevice));
+    const int32_t* base = static_cast<const int32_t*>(p->d_blob);
+    PlanDev& d = p->dev;
+    d.nN = p->nN; d.nE = p->nE; d.sumdof = p->sumdof; d.n = p->n; d.hbw = p->hbw; d.nslots = p->nslots;
+    d.npad = p->npad; d.LD = p->LD;
+    d.conn = base + off[0];
+    d.free_of_pos = base + off[1];
+    d.pos_of_free = base + off[2];
+    d.slot_ptr = base + off[3];
+    d.contrib = base + off[4];
+    d.node_ptr = base + off[5];
+    d.node_inc = base + off[6];
+    d.lumped = reinterpret_cast<const uint8_t*>(base + off[7]);
+    p->uploaded = true;
+    p->device = dev;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+namespace {
+
+struct BatchArgs {
+    long long B;
+    int C, do_static, do_modal, n_modes, max_sweeps;
+    const double *coords, *props, *nodal_mass, *f_nodal, *r_local;   // inputs
+    const double *Kb_in, *Mb_in;                                     // unfused: bands from HBM
+    double *Kb_out, *Mb_out;                                         // K2 outputs
+    double *u, *endforces, *reactions, *lam, *phi;
+    int32_t *info, *sweeps;
+};
+
+__device__ __forceinline__ void copy_in(double* dst, const double* src, int count, int tid, int nt) {
+    for (int i = tid; i < count; i += nt) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void fill_nan(double* dst, long long count, int tid, int nt) {
+    if (dst == nullptr) return;
+    const double q = __longlong_as_double(0x7ff8000000000000LL);
+    for (long long i = tid; i < count; i += nt) dst[i] = q;
+}
+
+// ---- K1: one thread per element, SoA in, [nE,6,6] out staged through shared memory so that the
+//      global stores are fully coalesced 16-byte vectors. ------------------------------------------
+constexpr int K1_WARPS = 4;
+constexpr int K1_PITCH = 38;   // doubles per element in the staging buffer (even: keeps 16 B alignment,
+                               // 38 mod 16 = 6 -> at most 2-way bank conflicts on the staging writes)
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k_element_km(long long nE, const double* __restrict__ xi, const double* __restrict__ yi,
+             const double* __restrict__ xj, const double* __restrict__ yj, const double* __restrict__ E,
+             const double* __restrict__ A, const double* __restrict__ I, const double* __restrict__ rho,
+             const uint8_t* __restrict__ lumped, double* __restrict__ Kg, double* __restrict__ Mg) {
+    __shared__ __align__(16) double stage[K1_WARPS][32 * K1_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* buf = stage[warp];
+    const long long warps_total = (long long)gridDim.x * K1_WARPS;
+    for (long long base = ((long long)blockIdx.x * K1_WARPS + warp) * 32; base < nE; base += warps_total * 32) {
+        const long long e = base + lane;
+        const bool ok = e < nE;
+        double L = 1.0, c = 1.0, s = 0.0, Ee = 0.0, Ae = 0.0, Ie = 0.0, re = 0.0;
+        bool lump = false;
+        if (ok) {
+            beam_geometry(xi[e], yi[e], xj[e], yj[e], L, c, s);
+            Ee = E[e]; Ae = A[e]; Ie = I[e]; re = rho[e];
+            lump = lumped != nullptr && lumped[e] != 0;
+        }
+        const int cnt = (int)min((long long)32, nE - base);     // elements in this warp tile
+        double X[6][6];
+        // ---- K
+        ke_local(X, Ee, Ae, Ie, L);
+        rotate_to_global(X, c, s);
+        // lane-major staging: element `lane` occupies doubles [lane*K1_PITCH, +36)
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) buf[lane * K1_PITCH + 6 * r + q] = X[r][q];
+        __syncwarp();
+        {
+            double2* dst = reinterpret_cast<double2*>(Kg + base * 36);
+            const double2* src = reinterpret_cast<const double2*>(buf);
+            for (int i = lane; i < cnt * 18; i += 32) {
+                const int el = i / 18;
+                dst[i] = src[el * (K1_PITCH / 2) + (i - el * 18)];
+            }
+        }
+        __syncwarp();
+        // ---- M
+        me_local(X, re, Ae, L, lump);
+        rotate_to_global(X, c, s);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) buf[lane * K1_PITCH + 6 * r + q] = X[r][q];
+        __syncwarp();
+        {
+            double2* dst = reinterpret_cast<double2*>(Mg + base * 36);
+            const double2* src = reinterpret_cast<const double2*>(buf);
+            for (int i = lane; i < cnt * 18; i += 32) {
+                const int el = i / 18;
+                dst[i] = src[el * (K1_PITCH / 2) + (i - el * 18)];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K2: assembly only: bands to HBM ----------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_assemble(PlanDev P, BatchArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const SmemLayout L = make_layout(P.nN, P.nE, P.n, P.hbw, P.npad, P.LD, 0);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const bool want_mass = A.Mb_out != nullptr;
+    for (long long b = blockIdx.x; b < A.B; b += gridDim.x) {
+        copy_in(smem + L.coords, A.coords + b * 2 * P.nN, 2 * P.nN, tid, nt);
+        copy_in(smem + L.props, A.props + b * 4 * P.nE, 4 * P.nE, tid, nt);
+        if (A.nodal_mass != nullptr) copy_in(smem + L.mass, A.nodal_mass + b * 2 * P.nN, 2 * P.nN, tid, nt);
+        __syncthreads();
+        stage_elements(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 36 * P.nE,
+                       want_mass, tid, nt);
+        __syncthreads();
+        stage_assemble(P, smem + L.U, smem + L.U + 36 * P.nE, A.nodal_mass ? smem + L.mass : nullptr,
+                       smem + L.Kb, smem + L.Mb, want_mass, tid, nt);
+        __syncthreads();
+        for (int i = tid; i < P.nslots; i += nt) {
+            A.Kb_out[b * P.nslots + i] = smem[L.Kb + i];
+            if (want_mass) A.Mb_out[b * P.nslots + i] = smem[L.Mb + i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
+//   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
+//   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE>
+__global__ void __launch_bounds__(NT, MINB)
+k_solve(PlanDev P, BatchArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const SmemLayout L = make_layout(P.nN, P.nE, P.n, P.hbw, P.npad, P.LD, A.C);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const long long b = blockIdx.x;
+    const int n = P.n;
+    int* s_order = reinterpret_cast<int*>(smem + L.order);
+    int* s_flag = s_order + P.npad;                  // [0] = K cholesky info, [1] = M cholesky info
+
+    const bool need_geo = ASSEMBLE || A.do_static;
+    if (need_geo) {
+        copy_in(smem + L.coords, A.coords + b * 2 * P.nN, 2 * P.nN, tid, nt);
+        copy_in(smem + L.props, A.props + b * 4 * P.nE, 4 * P.nE, tid, nt);
+    }
+    if (ASSEMBLE && A.do_modal && A.nodal_mass != nullptr)
+        copy_in(smem + L.mass, A.nodal_mass + b * 2 * P.nN, 2 * P.nN, tid, nt);
+    if (!ASSEMBLE) {
+        copy_in(smem + L.Kb, A.Kb_in + b * P.nslots, P.nslots, tid, nt);
+        if (A.do_modal) copy_in(smem + L.Mb, A.Mb_in + b * P.nslots, P.nslots, tid, nt);
+    }
+    if (tid < 2) s_flag[tid] = 0;
+    __syncthreads();
+    if (ASSEMBLE) {
+        stage_elements(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 36 * P.nE,
+                       A.do_modal != 0, tid, nt);
+        __syncthreads();
+        stage_assemble(P, smem + L.U, smem + L.U + 36 * P.nE,
+                       (A.do_modal && A.nodal_mass) ? smem + L.mass : nullptr, smem + L.Kb, smem + L.Mb,
+                       A.do_modal != 0, tid, nt);
+        __syncthreads();
+    } else if (A.do_static) {
+        stage_geometry(P, smem + L.coords, smem + L.geo, tid, nt);
+    }
+    // band Cholesky: warp 0 -> K, warp 1 -> M (concurrently)
+    if (warp == 0) {
+        const int r = band_cholesky_warp(smem + L.Kb, smem + L.invK, n, P.hbw, lane);
+        if (lane == 0) s_flag[0] = r;
+    } else if (warp == 1 && A.do_modal) {
+        const int r = band_cholesky_warp(smem + L.Mb, smem + L.invM, n, P.hbw, lane);
+        if (lane == 0) s_flag[1] = r;
+    }
+    __syncthreads();
+    const int infoK = s_flag[0], infoM = s_flag[1];
+    if (infoK != 0 || infoM != 0) {                  // numerical failure: NaN outputs, per-structure info
+        if (tid == 0) {
+            A.info[b] = infoK != 0 ? infoK : -1;
+            if (A.sweeps) A.sweeps[b] = 0;
+        }
+        if (A.do_static) {
+            fill_nan(A.u ? A.u + b * A.C * P.sumdof : nullptr, (long long)A.C * P.sumdof, tid, nt);
+            fill_nan(A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr, (long long)A.C * P.nE * 6, tid, nt);
+            fill_nan(A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, (long long)A.C * P.sumdof, tid, nt);
+        }
+        if (A.do_modal) {
+            fill_nan(A.lam + b * n, n, tid, nt);
+            fill_nan(A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, (long long)A.n_modes * P.sumdof, tid, nt);
+        }
+        return;
+    }
+    int info = 0;
+    if (A.do_static) {
+        double* s_f = smem + L.U;
+        double* s_ufull = s_f + A.C * n;
+        double* s_ef = s_ufull + A.C * P.sumdof;
+        stage_static(P, A.C, smem + L.props, smem + L.geo, smem + L.Kb, smem + L.invK, s_f, s_ufull, s_ef,
+                     A.f_nodal + b * A.C * P.sumdof,
+                     A.r_local ? A.r_local + b * A.C * P.nE * 6 : nullptr,
+                     A.u + b * A.C * P.sumdof,
+                     A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr,
+                     A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt);
+        __syncthreads();
+    }
+    if (A.do_modal) {
+        double* s_W = smem + L.U;
+        stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
+        const int sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
+        if (sw < 0) info = -2;
+        if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
+        stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,
+                                A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, tid, nt);
+    } else if (tid == 0 && A.sweeps) {
+        A.sweeps[b] = 0;
+    }
+    if (tid == 0) A.info[b] = info;
+}
+
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE>
+int launch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
+    const size_t bytes = (size_t)L.total * sizeof(double);
+    if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
+    auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE>;
+    BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (A.B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
+    kern<<<(unsigned)A.B, NT, bytes, stream>>>(plan->dev, A);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <bool ASSEMBLE>
+int dispatch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+    if (plan->rpl == 5 && plan->lpp == 2) return launch_solve<5, 2, 64, 8, ASSEMBLE>(plan, A, stream);
+    if (plan->rpl == 15 && plan->lpp == 2) return launch_solve<15, 2, 64, 8, ASSEMBLE>(plan, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 2) return launch_solve<29, 2, 64, 6, ASSEMBLE>(plan, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE>(plan, A, stream);
+    return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int bfe2_version(void) { return BFE2_VERSION; }
+
+const char* bfe2_last_error(void) { return g_err.c_str(); }
+
+int bfe2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int32_t* conn,
+                     int32_t n_fixed, const int32_t* fixed_pos, const uint8_t* lumped) {
+    if (!out) return fail(-1, "out is NULL");
+    *out = nullptr;
+    if (n_nodes < 2 || n_elem < 1 || !conn) return fail(-1, "need at least 2 nodes and 1 beam");
+    if (n_fixed < 0 || (n_fixed > 0 && !fixed_pos)) return fail(-1, "bad fixed_pos");
+    bfe2_plan* p = new bfe2_plan();
+    p->nN = n_nodes; p->nE = n_elem; p->sumdof = 3 * n_nodes;
+    p->conn.assign(conn, conn + 2 * (size_t)n_elem);
+    std::vector<char> seen(n_nodes, 0);
+    for (int e = 0; e < n_elem; ++e) {
+        const int i = conn[2 * e], j = conn[2 * e + 1];
+        if (i < 0 || j < 0 || i >= n_nodes || j >= n_nodes || i == j) {
+            delete p;
+            return fail(-1, "beam %d has invalid node indices (%d, %d)", e, i, j);
+        }
+        seen[i] = seen[j] = 1;
+    }
+    for (int k = 0; k < n_nodes; ++k)
+        if (!seen[k]) {   // Structure.node_numbering_is_ok (Structure.py:334-341): IDs must be 1..N, all used
+            delete p;
+            return fail(-1, "node %d is not attached to any beam (node numbering must be contiguous)", k + 1);
+        }
+    p->fixed.assign(fixed_pos, fixed_pos + n_fixed);
+    std::sort(p->fixed.begin(), p->fixed.end());                       // Structure.py:180
+    for (int k = 0; k < n_fixed; ++k) {
+        if (p->fixed[k] < 0 || p->fixed[k] >= p->sumdof || (k > 0 && p->fixed[k] == p->fixed[k - 1])) {
+            delete p;
+            return fail(-1, "fixed position %d out of range or duplicated", p->fixed[k]);
+        }
+    }
+    p->free_of_pos.assign(p->sumdof, 0);
+    for (int f : p->fixed) p->free_of_pos[f] = -1;
+    p->n = 0;
+    for (int pos = 0; pos < p->sumdof; ++pos)
+        if (p->free_of_pos[pos] == 0) { p->free_of_pos[pos] = p->n++; p->pos_of_free.push_back(pos); }
+    if (p->n == 0) { delete p; return fail(-1, "no free DOF left"); }
+    // half bandwidth in free numbering
+    p->hbw = 0;
+    for (int e = 0; e < n_elem; ++e) {
+        int lo = 1 << 30, hi = -1;
+        for (int a = 0; a < 6; ++a) {
+            const int f = p->free_of_pos[3 * conn[2 * e + a / 3] + a % 3];
+            if (f >= 0) { lo = std::min(lo, f); hi = std::max(hi, f); }
+        }
+        if (hi >= 0) p->hbw = std::max(p->hbw, hi - lo);
+    }
+    p->nslots = (p->hbw + 1) * p->n;
+    // scatter plan: slot (d, j) <- e*36 + r*6 + c for every lower-triangle contribution, beam order
+    std::vector<std::vector<int32_t>> lists(p->nslots);
+    for (int e = 0; e < n_elem; ++e)
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) {
+                const int fr = p->free_of_pos[3 * conn[2 * e + r / 3] + r % 3];   // helpers.py:28-31
+                const int fc = p->free_of_pos[3 * conn[2 * e + c / 3] + c % 3];
+                if (fr < 0 || fc < 0 || fr < fc) continue;
+                lists[(fr - fc) * p->n + fc].push_back(e * 36 + r * 6 + c);
+            }
+    p->slot_ptr.assign(p->nslots + 1, 0);
+    for (int s = 0; s < p->nslots; ++s) {
+        p->slot_ptr[s + 1] = p->slot_ptr[s] + (int)lists[s].size();
+        p->contrib.insert(p->contrib.end(), lists[s].begin(), lists[s].end());
+    }
+    p->ncontrib = (int)p->contrib.size();
+    // node -> incident beam ends, beam order
+    std::vector<std::vector<int32_t>> inc(n_nodes);
+    for (int e = 0; e < n_elem; ++e) {
+        inc[conn[2 * e]].push_back(2 * e);
+        inc[conn[2 * e + 1]].push_back(2 * e + 1);
+    }
+    p->node_ptr.assign(n_nodes + 1, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        p->node_ptr[k + 1] = p->node_ptr[k] + (int)inc[k].size();
+        p->node_inc.insert(p->node_inc.end(), inc[k].begin(), inc[k].end());
+    }
+    p->lumped.assign(n_elem, 0);
+    if (lumped) p->lumped.assign(lumped, lumped + n_elem);
+    p->npad = p->n + (p->n & 1);
+    if (jacobi_config(p->n, &p->rpl, &p->lpp)) {
+        p->LD = p->rpl * p->lpp;
+        p->nthreads = std::max(64, ((p->npad / 2) * p->lpp + 31) / 32 * 32);
+    } else {
+        p->rpl = p->lpp = 0;          // static / assembly still work; modal is refused
+        p->LD = 0;
+        p->nthreads = 64;
+    }
+    *out = p;
+    return 0;
+}
+
+void bfe2_plan_destroy(bfe2_plan* plan) {
+    if (!plan) return;
+    if (plan->uploaded && plan->d_blob) cudaFree(plan->d_blob);
+    delete plan;
+}
+
+int bfe2_plan_dims(const bfe2_plan* p, int32_t* n_nodes, int32_t* n_elem, int32_t* sumdof, int32_t* n_free,
+                   int32_t* hbw, int32_t* n_contrib) {
+    if (!p) return fail(-1, "plan is NULL");
+    if (n_nodes) *n_nodes = p->nN;
+    if (n_elem) *n_elem = p->nE;
+    if (sumdof) *sumdof = p->sumdof;
+    if (n_free) *n_free = p->n;
+    if (hbw) *hbw = p->hbw;
+    if (n_contrib) *n_contrib = p->ncontrib;
+    return 0;
+}
+
+int bfe2_plan_get_array(const bfe2_plan* p, int which, int32_t* out, int64_t capacity) {
+    if (!p || !out) return fail(-1, "NULL argument");
+    const std::vector<int32_t>* v = nullptr;
+    switch (which) {
+        case BFE2_ARR_CONN: v = &p->conn; break;
+        case BFE2_ARR_FREE_OF_POS: v = &p->free_of_pos; break;
+        case BFE2_ARR_POS_OF_FREE: v = &p->pos_of_free; break;
+        case BFE2_ARR_FIXED: v = &p->fixed; break;
+        case BFE2_ARR_SLOT_PTR: v = &p->slot_ptr; break;
+        case BFE2_ARR_CONTRIB: v = &p->contrib; break;
+        case BFE2_ARR_NODE_PTR: v = &p->node_ptr; break;
+        case BFE2_ARR_NODE_INC: v = &p->node_inc; break;
+        default: return fail(-1, "unknown plan array %d", which);
+    }
+    if ((int64_t)v->size() > capacity) return fail(-1, "capacity %lld < %zu", (long long)capacity, v->size());
+    if (!v->empty()) memcpy(out, v->data(), v->size() * sizeof(int32_t));
+    return (int)v->size();
+}
+
+size_t bfe2_plan_smem_bytes(const bfe2_plan* p, int32_t C) {
+    if (!p) return 0;
+    const SmemLayout L = make_layout(p->nN, p->nE, p->n, p->hbw, p->npad, p->LD, C);
+    return (size_t)L.total * sizeof(double);
+}
+
+size_t bfe2_workspace_bytes(const bfe2_plan*, int64_t) { return 0; }
+
+int bfe2_element_km(int64_t nE, const double* xi, const double* yi, const double* xj, const double* yj,
+                    const double* E, const double* A, const double* I, const double* rho,
+                    const uint8_t* lumped, double* Kg, double* Mg, void* stream) {
+    if (nE < 0 || !xi || !yi || !xj || !yj || !E || !A || !I || !rho || !Kg || !Mg)
+        return fail(-1, "bfe2_element_km: NULL argument");
+    if (nE == 0) return 0;
+    int dev = 0, sms = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (nE + 31) / 32;
+    const long long want = (tiles + K1_WARPS - 1) / K1_WARPS;
+    const int grid = (int)std::min<long long>(want, (long long)sms * 3 * 8);   // 3 resident blocks/SM, 8 waves
+    k_element_km<<<grid, K1_WARPS * 32, 0, (cudaStream_t)stream>>>(nE, xi, yi, xj, yj, E, A, I, rho, lumped, Kg, Mg);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const double* props,
+                         const double* nodal_mass, double* Kb, double* Mb, void* stream) {
+    if (!plan || B < 0 || !coords || !props || !Kb) return fail(-1, "bfe2_assemble_banded: bad argument");
+    if (B == 0) return 0;
+    if (int r = plan_upload(plan)) return r;
+    BatchArgs A{};
+    A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
+    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, 0);
+    const size_t bytes = (size_t)L.total * sizeof(double);
+    if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
+    BFE2_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int dev = 0, sms = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<long long>(B, (long long)sms * 16);
+    PlanDev P = plan->dev;
+    P.npad = 0; P.LD = 0;                              // no Jacobi region needed
+    k_assemble<<<grid, 64, bytes, (cudaStream_t)stream>>>(P, A);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, const double* coords,
+                      const double* props, const double* f_nodal, const double* r_local, double* u,
+                      double* endforces, double* reactions, int32_t* info, void* stream) {
+    if (!plan || B < 0 || C < 1 || !Kb || !coords || !props || !f_nodal || !u || !info)
+        return fail(-1, "bfe2_static_solve: bad argument");
+    if (B == 0) return 0;
+    if (int r = plan_upload(plan)) return r;
+    BatchArgs A{};
+    A.B = B; A.C = C; A.do_static = 1; A.do_modal = 0; A.max_sweeps = BFE2_MAX_SWEEPS;
+    A.coords = coords; A.props = props; A.f_nodal = f_nodal; A.r_local = r_local; A.Kb_in = Kb;
+    A.u = u; A.endforces = endforces; A.reactions = reactions; A.info = info;
+    // the static-only kernel does not need the Jacobi lanes: smallest instantiation, no W region
+    PlanDev P = plan->dev;
+    P.npad = 0; P.LD = 0;
+    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
+    const size_t bytes = (size_t)L.total * sizeof(double);
+    if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
+    auto kern = k_solve<5, 2, 64, 8, false>;
+    BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
+    kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bfe2_modal_solve(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Kb, const double* Mb,
+                     double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream) {
+    if (!plan || B < 0 || !Kb || !Mb || !lam || !info) return fail(-1, "bfe2_modal_solve: bad argument");
+    if (n_modes < 0 || n_modes > plan->n || (n_modes > 0 && !phi)) return fail(-1, "bad n_modes");
+    if (plan->rpl == 0) return fail(-3, "n_free = %d is beyond the Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
+    if (B == 0) return 0;
+    if (int r = plan_upload(plan)) return r;
+    BatchArgs A{};
+    A.B = B; A.C = 0; A.do_static = 0; A.do_modal = 1; A.n_modes = n_modes; A.max_sweeps = BFE2_MAX_SWEEPS;
+    A.Kb_in = Kb; A.Mb_in = Mb; A.lam = lam; A.phi = phi; A.info = info; A.sweeps = sweeps;
+    return dispatch_solve<false>(plan, A, (cudaStream_t)stream);
+}
+
+int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, int32_t n_modes,
+                     const double* coords, const double* props, const double* nodal_mass,
+                     const double* f_nodal, const double* r_local, double* u, double* endforces,
+                     double* reactions, double* lam, double* phi, int32_t* info, int32_t* sweeps,
+                     void* stream) {
+    if (!plan || B < 0 || C < 0 || !coords || !props || !info) return fail(-1, "bfe2_solve_fused: bad argument");
+    if (C > 0 && (!f_nodal || !u)) return fail(-1, "static outputs requested without f_nodal / u");
+    if (C == 0 && !do_modal) return fail(-1, "nothing to do");
+    if (do_modal) {
+        if (!lam) return fail(-1, "lam is NULL");
+        if (n_modes < 0 || n_modes > plan->n || (n_modes > 0 && !phi)) return fail(-1, "bad n_modes");
+        if (plan->rpl == 0)
+            return fail(-3, "n_free = %d is beyond the Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
+    }
+    if (B == 0) return 0;
+    if (int r = plan_upload(plan)) return r;
+    BatchArgs A{};
+    A.B = B; A.C = C; A.do_static = C > 0; A.do_modal = do_modal != 0; A.n_modes = do_modal ? n_modes : 0;
+    A.max_sweeps = BFE2_MAX_SWEEPS;
+    A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.f_nodal = f_nodal; A.r_local = r_local;
+    A.u = u; A.endforces = endforces; A.reactions = reactions; A.lam = lam; A.phi = phi;
+    A.info = info; A.sweeps = sweeps;
+    if (!do_modal) {
+        PlanDev P = plan->dev;
+        P.npad = 0; P.LD = 0;
+        const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
+        const size_t bytes = (size_t)L.total * sizeof(double);
+        if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
+        auto kern = k_solve<5, 2, 64, 8, true>;
+        BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
+        kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
+        BFE2_CUDA(cudaGetLastError());
+        return 0;
+    }
+    return dispatch_solve<true>(plan, A, (cudaStream_t)stream);
+}
+
+}  // extern "C"

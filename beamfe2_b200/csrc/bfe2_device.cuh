@@ -1,0 +1,508 @@
+// bfe2_device.cuh -- per-structure device routines shared by the unfused (K1..K4) and fused kernels.
+//
+// One thread block owns one structure variant; everything between the input loads and the output
+// stores lives in shared memory / registers.  Reference citations are file:line in jkbgbr/BeamFE2.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace bfe2 {
+
+// ------------------------------------------------------------------------------------------------
+// Device view of the topology plan (integer maps, built on the host in bfe2_plan.cpp-part of bfe2.cu)
+// ------------------------------------------------------------------------------------------------
+struct PlanDev {
+    int nN, nE, sumdof, n, hbw;   // nodes, beams, 3*nN, free DOFs, half bandwidth (free numbering)
+    int nslots;                   // (hbw+1)*n band slots
+    int npad, LD;                 // Jacobi: even slot count >= n, leading dimension (rows, padded)
+    const int32_t* conn;          // [nE*2]
+    const int32_t* free_of_pos;   // [sumdof]
+    const int32_t* pos_of_free;   // [n]
+    const int32_t* slot_ptr;      // [nslots+1]
+    const int32_t* contrib;       // [ncontrib]  e*36 + r*6 + c
+    const int32_t* node_ptr;      // [nN+1]
+    const int32_t* node_inc;      // [2*nE]      e*2 + end
+    const uint8_t* lumped;        // [nE]
+};
+
+// Shared-memory carve-up (offsets in doubles from the dynamic smem base).  Region U is a union:
+//   phase "elements/assembly": Ke[36 nE], Me[36 nE]
+//   phase "static":            f[C n], ufull[C sumdof], ef[C nE 6]
+//   phase "modal":             W[npad * LD]
+struct SmemLayout {
+    int coords, props, mass, geo, Kb, Mb, invK, invM, U, lam, order, total;
+};
+
+__host__ __device__ inline int imax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+__host__ __device__ inline SmemLayout make_layout(int nN, int nE, int n, int hbw, int npad, int LD, int C) {
+    SmemLayout L;
+    int o = 0;
+    L.coords = o; o += 2 * nN;
+    L.props = o;  o += 4 * nE;
+    L.mass = o;   o += 2 * nN;
+    L.geo = o;    o += 3 * nE;
+    L.Kb = o;     o += (hbw + 1) * n;
+    L.Mb = o;     o += (hbw + 1) * n;
+    L.invK = o;   o += n;
+    L.invM = o;   o += n;
+    o = (o + 1) & ~1;                                   // 16-byte align the big region
+    L.U = o;
+    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), npad * LD);
+    L.lam = o;    o += npad;
+    L.order = o;  o += (npad + 1) / 2 + 1;              // npad int32 + 2 flags, stored in double slots
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Element level
+// ------------------------------------------------------------------------------------------------
+
+// Local stiffness, HermitianBeam_2D.py:284-297.  DOF order [ux_i, uy_i, rz_i, ux_j, uy_j, rz_j].
+__device__ __forceinline__ void ke_local(double X[6][6], double E, double A, double I, double L) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) X[r][c] = 0.0;
+    const double EA = E * A, EI = E * I;
+    const double a = EA / L;
+    const double b12 = 12.0 * EI / (L * L * L);
+    const double b6 = 6.0 * EI / (L * L);
+    const double b4 = 4.0 * EI / L;
+    const double b2 = 2.0 * EI / L;
+    X[0][0] = X[3][3] = a;
+    X[0][3] = X[3][0] = -a;
+    X[1][1] = X[4][4] = b12;
+    X[1][4] = X[4][1] = -b12;
+    X[1][2] = X[2][1] = X[1][5] = X[5][1] = b6;
+    X[2][4] = X[4][2] = X[4][5] = X[5][4] = -b6;
+    X[2][2] = X[5][5] = b4;
+    X[2][5] = X[5][2] = b2;
+}
+
+// Local mass: consistent HermitianBeam_2D.py:233-249, lumped :225-231 (rotary terms m * 1e-10).
+__device__ __forceinline__ void me_local(double X[6][6], double rho, double A, double L, bool lumped) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) X[r][c] = 0.0;
+    if (lumped) {
+        const double m = 0.5 * A * L * rho;
+        X[0][0] = X[1][1] = X[3][3] = X[4][4] = m;
+        X[2][2] = X[5][5] = m * 1e-10;
+        return;
+    }
+    const double f = rho * A * L / 420.0;
+    X[0][0] = X[3][3] = f * 140.0;
+    X[0][3] = X[3][0] = f * 70.0;
+    X[1][1] = X[4][4] = f * 156.0;
+    X[1][2] = X[2][1] = f * (22.0 * L);
+    X[1][4] = X[4][1] = f * 54.0;
+    X[1][5] = X[5][1] = f * (-13.0 * L);
+    X[2][2] = X[5][5] = f * (4.0 * L * L);
+    X[2][4] = X[4][2] = f * (13.0 * L);
+    X[2][5] = X[5][2] = f * (-3.0 * L * L);
+    X[4][5] = X[5][4] = f * (-22.0 * L);
+}
+
+// X <- T X T^T with T = diag(R, R), R = [[c,-s,0],[s,c,0],[0,0,1]]  (helpers.py:43-69,
+// HermitianBeam_2D.py:173-175).  Same left-to-right evaluation order as the reference: rows first.
+__device__ __forceinline__ void rotate_to_global(double X[6][6], double c, double s) {
+#pragma unroll
+    for (int k = 0; k < 6; k += 3) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {               // Y = T X  (rows k, k+1)
+            const double a = X[k][j], b = X[k + 1][j];
+            X[k][j] = c * a - s * b;
+            X[k + 1][j] = s * a + c * b;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k += 3) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {               // Z = Y T^T (columns k, k+1)
+            const double a = X[i][k], b = X[i][k + 1];
+            X[i][k] = c * a - s * b;
+            X[i][k + 1] = s * a + c * b;
+        }
+    }
+}
+
+// Geometry of one beam: length HermitianBeam_2D.py:98-100; direction cosines of :114-120
+// (the reference takes cos/sin of arctan2(dy,dx); dx/L, dy/L are the same numbers to 1 ulp).
+__device__ __forceinline__ void beam_geometry(double xi, double yi, double xj, double yj,
+                                              double& L, double& c, double& s) {
+    const double dx = xj - xi, dy = yj - yi;
+    L = sqrt((xi - xj) * (xi - xj) + (yi - yj) * (yi - yj));
+    c = dx / L;
+    s = dy / L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level stages.  `tid`/`nt` = thread index / count inside the block.
+// ------------------------------------------------------------------------------------------------
+
+// Stage E: geometry + global 6x6 K and M of every beam into shared memory.
+__device__ __forceinline__ void stage_elements(const PlanDev& P, const double* s_coords, const double* s_props,
+                                               double* s_geo, double* s_Ke, double* s_Me, bool want_mass,
+                                               int tid, int nt) {
+    for (int e = tid; e < P.nE; e += nt) {
+        const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
+        double L, c, s;
+        beam_geometry(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], L, c, s);
+        s_geo[3 * e] = L;
+        s_geo[3 * e + 1] = c;
+        s_geo[3 * e + 2] = s;
+        const double E = s_props[4 * e], A = s_props[4 * e + 1], I = s_props[4 * e + 2], rho = s_props[4 * e + 3];
+        double X[6][6];
+        ke_local(X, E, A, I, L);
+        rotate_to_global(X, c, s);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s_Ke[36 * e + 6 * r + q] = X[r][q];
+        if (want_mass) {
+            me_local(X, rho, A, L, P.lumped[e] != 0);
+            rotate_to_global(X, c, s);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s_Me[36 * e + 6 * r + q] = X[r][q];
+        }
+    }
+}
+
+// Stage E': geometry only (the static kernel needs L, c, s for end forces but not the matrices).
+__device__ __forceinline__ void stage_geometry(const PlanDev& P, const double* s_coords, double* s_geo, int tid, int nt) {
+    for (int e = tid; e < P.nE; e += nt) {
+        const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
+        double L, c, s;
+        beam_geometry(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], L, c, s);
+        s_geo[3 * e] = L;
+        s_geo[3 * e + 1] = c;
+        s_geo[3 * e + 2] = s;
+    }
+}
+
+// Stage A: collision-free assembly of the condensed band matrices.  Every band slot (d, j) is owned
+// by one thread which adds its contributions in beam-list order -- the summation order of
+// helpers.py:19-39 -- so no atomics and a deterministic result.  Supported rows/columns are simply
+// not in the plan (Structure.condense, Structure.py:183-191); nodal masses go on the diagonal
+// (Structure.py:198-209; mx->ux, my->uy, no rotary term :289-313).
+__device__ __forceinline__ void stage_assemble(const PlanDev& P, const double* s_Ke, const double* s_Me,
+                                               const double* s_mass, double* s_Kb, double* s_Mb,
+                                               bool want_mass, int tid, int nt) {
+    for (int slot = tid; slot < P.nslots; slot += nt) {
+        const int p0 = P.slot_ptr[slot], p1 = P.slot_ptr[slot + 1];
+        double k = 0.0, m = 0.0;
+        for (int p = p0; p < p1; ++p) {
+            const int idx = P.contrib[p];
+            k += s_Ke[idx];
+            if (want_mass) m += s_Me[idx];
+        }
+        s_Kb[slot] = k;
+        if (want_mass) {
+            if (slot < P.n && s_mass != nullptr) {       // d == 0: diagonal
+                const int pos = P.pos_of_free[slot];
+                const int dof = pos % 3;
+                if (dof < 2) m += s_mass[2 * (pos / 3) + dof];
+            }
+            s_Mb[slot] = m;
+        }
+    }
+}
+
+// In-place banded Cholesky by ONE WARP.  Ab[d*n + j] = A[j+d][j], d = 0..b.  Returns 0 or the
+// 1-based column of the first non-positive pivot (uniform across the warp).  Also writes 1/L[j][j].
+__device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, int n, int b, int lane) {
+    for (int j = 0; j < n; ++j) {
+        const double ajj = Ab[j];
+        if (!(ajj > 0.0) || !isfinite(ajj)) return j + 1;
+        const double ljj = sqrt(ajj);
+        const double inv = 1.0 / ljj;
+        const int m = min(b, n - 1 - j);
+        __syncwarp();
+        if (lane == 0) { Ab[j] = ljj; invdiag[j] = inv; }
+        for (int d = 1 + lane; d <= m; d += 32) Ab[d * n + j] *= inv;
+        __syncwarp();
+        // trailing update: A[j+p][j+q] -= L[j+p][j] * L[j+q][j],  1 <= q <= p <= m
+        for (int t = lane; t < m * m; t += 32) {
+            const int p = t / m + 1, q = t % m + 1;
+            if (q <= p) Ab[(p - q) * n + j + q] -= Ab[p * n + j] * Ab[q * n + j];
+        }
+        __syncwarp();
+    }
+    return 0;
+}
+
+// Forward + back substitution with the band factor, one thread per right-hand side (in place).
+__device__ __forceinline__ void band_solve_thread(const double* Lb, const double* invdiag, double* x, int n, int b) {
+    for (int j = 0; j < n; ++j) {                    // L y = f
+        double acc = x[j];
+        const int m = min(b, j);
+        for (int d = 1; d <= m; ++d) acc -= Lb[d * n + (j - d)] * x[j - d];
+        x[j] = acc * invdiag[j];
+    }
+    for (int j = n - 1; j >= 0; --j) {               // L^T u = y
+        double acc = x[j];
+        const int m = min(b, n - 1 - j);
+        for (int d = 1; d <= m; ++d) acc -= Lb[d * n + j] * x[j + d];
+        x[j] = acc * invdiag[j];
+    }
+}
+
+// Back substitution only: L^T x = w (in place), one thread.
+__device__ __forceinline__ void band_backsolve_thread(const double* Lb, const double* invdiag, double* x, int n, int b) {
+    for (int j = n - 1; j >= 0; --j) {
+        double acc = x[j];
+        const int m = min(b, n - 1 - j);
+        for (int d = 1; d <= m; ++d) acc -= Lb[d * n + j] * x[j + d];
+        x[j] = acc * invdiag[j];
+    }
+}
+
+// Stage S: static solve for C load cases + end forces + reactions, results to global memory.
+//   f = f_nodal + sum_e T(alpha_e) r_local_e        (Structure.py:244-287, Loads.py:100-112)
+//   u = K^-1 f on the free DOFs, 0 at supports      (Solver.py:76-87 with condensation)
+//   endforces = Ke u_local - r_local                (Results.py:48-79, HermitianBeam_2D.py:336-351)
+//   reactions = sum_e R(alpha_e) endforces - f_nodal (Results.py:92-127)
+__device__ __forceinline__ void stage_static(const PlanDev& P, int C, const double* s_props, const double* s_geo,
+                                             const double* s_Kb, const double* s_invK,
+                                             double* s_f, double* s_ufull, double* s_ef,
+                                             const double* g_f_nodal, const double* g_r_local,
+                                             double* g_u, double* g_ef, double* g_react, int tid, int nt) {
+    const int n = P.n, sumdof = P.sumdof, nE = P.nE;
+    // 1. right-hand sides in free numbering
+    for (int t = tid; t < C * n; t += nt) {
+        const int c = t / n, j = t % n;
+        const int pos = P.pos_of_free[j];
+        double v = g_f_nodal[c * sumdof + pos];
+        if (g_r_local != nullptr) {
+            const int node = pos / 3, k = pos % 3;
+            for (int q = P.node_ptr[node]; q < P.node_ptr[node + 1]; ++q) {
+                const int inc = P.node_inc[q];
+                const int e = inc >> 1, end = inc & 1;
+                const double* r = g_r_local + ((size_t)c * nE + e) * 6 + 3 * end;
+                const double cs = s_geo[3 * e + 1], sn = s_geo[3 * e + 2];
+                if (k == 0) v += cs * r[0] - sn * r[1];
+                else if (k == 1) v += sn * r[0] + cs * r[1];
+                else v += r[2];
+            }
+        }
+        s_f[c * n + j] = v;
+    }
+    __syncthreads();
+    // 2. one thread per load case: L L^T u = f
+    for (int c = tid; c < C; c += nt) band_solve_thread(s_Kb, s_invK, s_f + c * n, n, P.hbw);
+    __syncthreads();
+    // 3. expand to all DOFs (exact zeros at supports), write u
+    for (int t = tid; t < C * sumdof; t += nt) {
+        const int c = t / sumdof, pos = t % sumdof;
+        const int j = P.free_of_pos[pos];
+        const double v = (j >= 0) ? s_f[c * n + j] : 0.0;
+        s_ufull[t] = v;
+        g_u[t] = v;
+    }
+    __syncthreads();
+    if (g_ef == nullptr && g_react == nullptr) return;
+    // 4. local end forces per (load case, beam)
+    for (int t = tid; t < C * nE; t += nt) {
+        const int c = t / nE, e = t % nE;
+        const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
+        const double L = s_geo[3 * e], cs = s_geo[3 * e + 1], sn = s_geo[3 * e + 2];
+        const double* ui = s_ufull + c * sumdof + 3 * ni;
+        const double* uj = s_ufull + c * sumdof + 3 * nj;
+        // u_local = R(-alpha) u  (Results.py:63-71)
+        const double d0 = cs * ui[0] + sn * ui[1], d1 = -sn * ui[0] + cs * ui[1], d2 = ui[2];
+        const double d3 = cs * uj[0] + sn * uj[1], d4 = -sn * uj[0] + cs * uj[1], d5 = uj[2];
+        const double E = s_props[4 * e], A = s_props[4 * e + 1], I = s_props[4 * e + 2];
+        const double EA = E * A, EI = E * I;
+        const double a = EA / L, b12 = 12.0 * EI / (L * L * L), b6 = 6.0 * EI / (L * L);
+        const double b4 = 4.0 * EI / L, b2 = 2.0 * EI / L;
+        double q[6];
+        q[0] = a * d0 - a * d3;
+        q[1] = b12 * d1 + b6 * d2 - b12 * d4 + b6 * d5;
+        q[2] = b6 * d1 + b4 * d2 - b6 * d4 + b2 * d5;
+        q[3] = -a * d0 + a * d3;
+        q[4] = -b12 * d1 - b6 * d2 + b12 * d4 - b6 * d5;
+        q[5] = b6 * d1 + b2 * d2 - b6 * d4 + b4 * d5;
+        if (g_r_local != nullptr) {
+            const double* r = g_r_local + ((size_t)c * nE + e) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) q[k] -= r[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_ef[t * 6 + k] = q[k];
+        if (g_ef != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) g_ef[(size_t)t * 6 + k] = q[k];
+        }
+    }
+    if (g_react == nullptr) return;
+    __syncthreads();
+    // 5. global reactions per (load case, position)
+    for (int t = tid; t < C * sumdof; t += nt) {
+        const int c = t / sumdof, pos = t % sumdof;
+        const int node = pos / 3, k = pos % 3;
+        double v = 0.0;
+        for (int q = P.node_ptr[node]; q < P.node_ptr[node + 1]; ++q) {
+            const int inc = P.node_inc[q];
+            const int e = inc >> 1, end = inc & 1;
+            const double* f = s_ef + ((size_t)c * nE + e) * 6 + 3 * end;
+            const double cs = s_geo[3 * e + 1], sn = s_geo[3 * e + 2];
+            if (k == 0) v += cs * f[0] - sn * f[1];
+            else if (k == 1) v += sn * f[0] + cs * f[1];
+            else v += f[2];
+        }
+        g_react[t] = v - g_f_nodal[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage M: generalized eigenproblem K phi = lam M phi  (scipy.linalg.eigh(K, M), Solver.py:39).
+//
+//   K = Lk Lk^T, M = Lm Lm^T (band Cholesky, done by the caller);  G = Lm^-1 Lk
+//   standard form C = Lm^-1 K Lm^-T = G G^T.  The cyclic Jacobi method is applied ONE-SIDED to the
+//   factor: W = G^T V, rotating column pairs of W until they are mutually orthogonal, which is the
+//   Jacobi diagonalisation of C = (G^T)^T (G^T) without ever forming C (Veselic/Hari: the small
+//   eigenvalues keep their relative accuracy).  At convergence  lam_k = |w_k|^2  and
+//   phi_k = Lk^-T w_k  satisfies  K phi = lam M phi  with  phi^T M phi = 1  (scipy's normalisation).
+//
+//   Parallel ordering: round-robin tournament on npad (even) fixed SLOTS; pair p works on slots
+//   (p, npad-1-p); after every step the contents of slots 1..npad-1 rotate by one position, which the
+//   pair does by storing its two updated columns to the shifted slots.  When n is odd slot 0 holds
+//   a zero dummy column.  LPP lanes share a pair (each holds RPL rows of both columns in registers).
+// ------------------------------------------------------------------------------------------------
+#define BFE2_JACOBI_TOL 1.0e-15
+
+template <int RPL, int LPP>
+__device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
+    const int npad = P.npad, LD = P.LD;
+    const int npairs = npad >> 1;
+    const int pr = tid / LPP, h = tid % LPP;
+    const bool active = pr < npairs;
+    const int st = active ? pr : 0;
+    const int sb = active ? (npad - 1 - pr) : 0;
+    const int dt = (st >= 1) ? st + 1 : 0;
+    const int db = (sb < npad - 1) ? sb + 1 : 1;
+    const double* src_t = s_W + st * LD + h * RPL;
+    const double* src_b = s_W + sb * LD + h * RPL;
+    double* dst_t = s_W + dt * LD + h * RPL;
+    double* dst_b = s_W + db * LD + h * RPL;
+
+    double x[RPL], y[RPL];
+    int sweeps = 0;
+    bool converged = false;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        int rotated = 0;
+        for (int step = 0; step < npad - 1; ++step) {
+            double a = 0.0, b = 0.0, g = 0.0;
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) { x[r] = src_t[r]; y[r] = src_b[r]; }
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    a = fma(x[r], x[r], a);
+                    b = fma(y[r], y[r], b);
+                    g = fma(x[r], y[r], g);
+                }
+            }
+#pragma unroll
+            for (int m = 1; m < LPP; m <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, m);
+                b += __shfl_xor_sync(0xffffffffu, b, m);
+                g += __shfl_xor_sync(0xffffffffu, g, m);
+            }
+            __syncthreads();                       // every pair has read its slots
+            if (active) {
+                if (fabs(g) > BFE2_JACOBI_TOL * sqrt(a * b)) {
+                    rotated = 1;
+                    const double zeta = (b - a) / (2.0 * g);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t);
+                    const double s = c * t;
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        const double xr = x[r], yr = y[r];
+                        x[r] = c * xr - s * yr;
+                        y[r] = s * xr + c * yr;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) { dst_t[r] = x[r]; dst_b[r] = y[r]; }
+            }
+            __syncthreads();                       // shifted slots visible before the next step
+        }
+        if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
+    }
+    return converged ? sweeps : -sweeps;           // negative: not converged within max_sweeps
+}
+
+// Form W = G^T in the slot layout:  slot (k + off) holds row k of G = Lm^-1 Lk, off = npad - n.
+// Thread j owns column j of G (forward substitution with the band factor Lm).
+__device__ __forceinline__ void stage_form_gt(const PlanDev& P, const double* s_Kb, const double* s_Mb,
+                                              const double* s_invM, double* s_W, int tid, int nt) {
+    const int n = P.n, b = P.hbw, LD = P.LD, off = P.npad - P.n;
+    for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
+    __syncthreads();
+    for (int j = tid; j < n; j += nt) {
+        for (int r = j; r < n; ++r) {
+            double acc = (r - j <= b) ? s_Kb[(r - j) * n + j] : 0.0;
+            const int k0 = max(j, r - b);
+            for (int k = k0; k < r; ++k) acc -= s_Mb[(r - k) * n + k] * s_W[(k + off) * LD + j];
+            s_W[(r + off) * LD + j] = acc * s_invM[r];
+        }
+    }
+    __syncthreads();
+}
+
+// After convergence: eigenvalues (ascending) and the first n_modes shapes to global memory.
+template <int LPP>
+__device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
+                                                   double* s_W, double* s_lam, int* s_order, int n_modes,
+                                                   double* g_lam, double* g_phi, int tid, int nt) {
+    const int n = P.n, npad = P.npad, LD = P.LD;
+    // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
+    for (int s = tid; s < npad; s += nt) {
+        double acc = 0.0;
+        const double* w = s_W + s * LD;
+        for (int r = 0; r < n; ++r) acc = fma(w[r], w[r], acc);
+        s_lam[s] = (npad != n && s == 0) ? INFINITY : acc;
+    }
+    __syncthreads();
+    for (int s = tid; s < npad; s += nt) {
+        const double v = s_lam[s];
+        int rank = 0;
+        for (int q = 0; q < npad; ++q) {
+            const double w = s_lam[q];
+            rank += (w < v || (w == v && q < s)) ? 1 : 0;
+        }
+        s_order[rank] = s;
+        if (rank < n) g_lam[rank] = v;
+    }
+    __syncthreads();
+    if (n_modes <= 0 || g_phi == nullptr) return;
+    // phi = Lk^-T w, in place in the slot; then fix the sign (largest-magnitude entry positive)
+    for (int m = tid; m < n_modes; m += nt) {
+        double* w = s_W + s_order[m] * LD;
+        band_backsolve_thread(s_Kb, s_invK, w, n, P.hbw);
+        double best = 0.0, sign = 1.0;
+        for (int r = 0; r < n; ++r) {
+            const double v = fabs(w[r]);
+            if (v > best) { best = v; sign = (w[r] < 0.0) ? -1.0 : 1.0; }
+        }
+        if (sign < 0.0)
+            for (int r = 0; r < n; ++r) w[r] = -w[r];
+    }
+    __syncthreads();
+    for (int t = tid; t < n_modes * P.sumdof; t += nt) {
+        const int m = t / P.sumdof, pos = t % P.sumdof;
+        const int j = P.free_of_pos[pos];
+        g_phi[t] = (j >= 0) ? s_W[s_order[m] * LD + j] : 0.0;
+    }
+}
+
+}  // namespace bfe2

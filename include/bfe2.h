@@ -1,0 +1,130 @@
+/*
+ * bfe2.h -- C ABI of libbfe2.so, the B200 (sm_100a) implementation of BeamFE2's numeric hot path.
+ *
+ * The reference (jkbgbr/BeamFE2) is pure Python and has no FFI layer; its operator boundary is the
+ * Solver contract  Solver(structure).solve() -> bool  (BeamFE2/Solver.py:16-21) which reads
+ * Structure.K_with_BC / M_with_masses / condense / load_vector (BeamFE2/Structure.py:183-236) and
+ * writes structure.results[...] (BeamFE2/Results.py:87-173).  The entry points below are what a
+ * ctypes binding placed inside those solve() methods would call; each one
+ * cites the reference code it replaces.  All file:line citations are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a CUDA DEVICE pointer to contiguous
+ *     float64 (or int32 / uint8 where stated) owned by the caller; outputs are fully overwritten.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync inside.
+ *   - return value: 0 = ok, negative = bad argument / CUDA failure (text via bfe2_last_error()).
+ *     Numerical failure is reported PER STRUCTURE in info[B]:
+ *        0  ok
+ *        k>0  non-positive Cholesky pivot of the condensed K at column k (1-based)
+ *             == the reference's "stiffness matrix is singular" (Structure.py:325-354)
+ *        -1  condensed mass matrix not positive definite / all-zero (Solver.py:34-35 returns False)
+ *        -2  Jacobi did not converge in BFE2_MAX_SWEEPS sweeps
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with -100.
+ *
+ * Layout of the per-variant tensors (B = number of structure variants sharing one topology plan,
+ * C = number of load cases, nN nodes, nE beams, sumdof = 3 nN, n = number of free DOFs, hbw = half
+ * bandwidth of the condensed matrices in free-DOF numbering):
+ *     coords      [B, nN, 2]      node coordinates (Node.py:31-37)
+ *     props       [B, nE, 4]      E, A, I, rho per beam (HermitianBeam_2D.py:42-67)
+ *     nodal_mass  [B, nN, 2]      mx, my per node or NULL (Structure.py:53-74, 289-313)
+ *     f_nodal     [B, C, sumdof]  directly applied nodal loads (Structure.py:76-97, 258-287)
+ *     r_local     [B, C, nE, 6]   per beam: sum of the LOCAL fixed-end vectors of its internal loads
+ *                                 (Loads.py reactions_asvector, :202-208, 264-270, 333-342, 409-416,
+ *                                 474-484) or NULL
+ *     Kb, Mb      [B, hbw+1, n]   lower band storage, Xb[d][j] = X[j+d, j] of the condensed matrix
+ *     u           [B, C, sumdof]  displacements, exact zeros at supported DOFs
+ *     endforces   [B, C, nE, 6]   local end forces Ke u_loc - r_local (HermitianBeam_2D.py:336-351)
+ *     reactions   [B, C, sumdof]  Results.py:92-127
+ *     lam         [B, n]          all eigenvalues, ascending (Solver.py:39)
+ *     phi         [B, n_modes, sumdof]  first n_modes M-normalised shapes, zeros at supports
+ *                                 (Solver.py:54-65); sign: the largest-magnitude entry is positive
+ */
+#ifndef BFE2_H
+#define BFE2_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFE2_VERSION 100          /* 0.1.0 */
+#define BFE2_MAX_SWEEPS 40
+#define BFE2_MAX_JACOBI_N 116     /* largest n_free the shared-memory Jacobi path accepts */
+
+typedef struct bfe2_plan bfe2_plan;
+
+/* plan integer arrays retrievable with bfe2_plan_get_array (for bit-exact DOF-map checks) */
+enum bfe2_plan_array {
+    BFE2_ARR_CONN = 0,          /* [nE*2]       0-based node indices (helpers.py:28-31 minus the *3) */
+    BFE2_ARR_FREE_OF_POS = 1,   /* [sumdof]     free index of a global position, -1 if supported   */
+    BFE2_ARR_POS_OF_FREE = 2,   /* [n]          global position of each free DOF (what np.delete keeps,
+                                                Structure.py:183-191)                               */
+    BFE2_ARR_FIXED = 3,         /* [nF]         == Structure.positions_to_eliminate (:164-181)       */
+    BFE2_ARR_SLOT_PTR = 4,      /* [(hbw+1)*n+1] CSR pointers of the band-slot scatter plan          */
+    BFE2_ARR_CONTRIB = 5,       /* [n_contrib]  e*36 + r*6 + c, beam-list order inside every slot    */
+    BFE2_ARR_NODE_PTR = 6,      /* [nN+1]       CSR pointers node -> incident (beam*2 + end)         */
+    BFE2_ARR_NODE_INC = 7       /* [2*nE]                                                            */
+};
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         bfe2_version(void);
+const char* bfe2_last_error(void);                 /* thread-local, never NULL */
+int         bfe2_device_count(void);               /* 0 when no usable CUDA device */
+
+/* ---- topology plan (replaces the DOF bookkeeping of Structure.py:154-191, 379-393 and the block
+ *      indexing of helpers.py:7-40; pure host code, no CUDA call until the first launch) -------- */
+int  bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem,
+                      const int32_t* conn /*[nE,2] 0-based*/,
+                      int32_t n_fixed, const int32_t* fixed_pos /* any order, no duplicates */,
+                      const uint8_t* lumped /*[nE] or NULL*/);
+void bfe2_plan_destroy(bfe2_plan* plan);
+int  bfe2_plan_dims(const bfe2_plan* plan, int32_t* n_nodes, int32_t* n_elem, int32_t* sumdof,
+                    int32_t* n_free, int32_t* hbw, int32_t* n_contrib);
+int  bfe2_plan_get_array(const bfe2_plan* plan, int which, int32_t* out, int64_t capacity);
+/* bytes of dynamic shared memory per structure the fused / modal kernels need for this plan */
+size_t bfe2_plan_smem_bytes(const bfe2_plan* plan, int32_t n_loadcases);
+/* caller-owned scratch needed by the entry points below for a batch of B (currently 0: everything
+ * lives in shared memory; kept so the ABI does not change when a global-memory path is added) */
+size_t bfe2_workspace_bytes(const bfe2_plan* plan, int64_t B);
+
+/* ---- K1: element kernel (HermitianBeam_2D.py:98-120, 225-249, 284-297; helpers.py:43-69;
+ *      matrix_in_global :173-175).  SoA inputs of nE_total elements, outputs [nE_total, 6, 6]. --- */
+int bfe2_element_km(int64_t n_elem_total,
+                    const double* xi, const double* yi, const double* xj, const double* yj,
+                    const double* E, const double* A, const double* I, const double* rho,
+                    const uint8_t* lumped /*or NULL*/, double* Kg, double* Mg, void* stream);
+
+/* ---- K2: banded assembly with support condensation and nodal masses
+ *      (helpers.py:7-40; Structure.py:183-209) ------------------------------------------------- */
+int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const double* props,
+                         const double* nodal_mass /*or NULL*/, double* Kb, double* Mb /*or NULL*/,
+                         void* stream);
+
+/* ---- K3: banded Cholesky + forward/back substitution, end forces, reactions
+ *      (Solver.py:76-87; Results.py:48-127; HermitianBeam_2D.py:336-351) ----------------------- */
+int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb,
+                      const double* coords, const double* props,
+                      const double* f_nodal, const double* r_local /*or NULL*/,
+                      double* u, double* endforces /*or NULL*/, double* reactions /*or NULL*/,
+                      int32_t* info, void* stream);
+
+/* ---- K4: generalized symmetric eigenproblem K phi = lam M phi, small n: Cholesky reduction +
+ *      batched one-sided Jacobi (Solver.py:29-69).  sweeps[B] (or NULL) receives the sweep count. */
+int bfe2_modal_solve(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Kb, const double* Mb,
+                     double* lam, double* phi /*or NULL when n_modes==0*/, int32_t* info,
+                     int32_t* sweeps /*or NULL*/, void* stream);
+
+/* ---- fused K1->K4: nothing but inputs and outputs touches HBM.  C may be 0 (modal only, the
+ *      static outputs may then be NULL); do_modal = 0 skips the eigenproblem. -------------------- */
+int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, int32_t n_modes,
+                     const double* coords, const double* props, const double* nodal_mass,
+                     const double* f_nodal, const double* r_local,
+                     double* u, double* endforces, double* reactions,
+                     double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFE2_H */
