@@ -135,3 +135,84 @@ def solve_fused(plan: Plan, coords, props, nodal_mass=None, f_nodal=None, r_loca
             _lib.ptr(nodal_mass), _lib.ptr(f_nodal), _lib.ptr(r_local), _lib.ptr(u), _lib.ptr(ef),
             _lib.ptr(re), _lib.ptr(lam), _lib.ptr(phi), _lib.ptr(info), _lib.ptr(sweeps), _stream_ptr()))
     return dict(u=u, endforces=ef, reactions=re, lam=lam, phi=phi, info=info, sweeps=sweeps)
+
+
+class HostPipeline:
+    """End-to-end path with HOST buffers: pinned host tensors -> H2D -> fused kernel -> D2H, chunked
+    over a few CUDA streams so that copies overlap the kernels.  This is the call a user of the
+    reference-facing API makes when the model data lives on the host (the reference keeps everything
+    in host numpy matrices, BeamFE2/Structure.py)."""
+
+    IN_KEYS = ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')
+    OUT_KEYS = ('u', 'endforces', 'reactions', 'lam', 'phi', 'info', 'sweeps')
+
+    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, chunk: int = 16384, n_streams: int = 3,
+                 device=None, modal: bool = True):
+        self.plan, self.C, self.modal = plan, int(n_loadcases), bool(modal)
+        self.n_modes = int(n_modes) if modal else 0
+        self.chunk = int(chunk)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        p, C = plan, self.C
+        self.in_shapes = dict(coords=(p.n_nodes, 2), props=(p.n_elem, 4), nodal_mass=(p.n_nodes, 2),
+                              f_nodal=(C, p.sumdof), r_local=(C, p.n_elem, 6))
+        self.out_shapes = dict(u=(C, p.sumdof), endforces=(C, p.n_elem, 6), reactions=(C, p.sumdof),
+                               lam=(p.n_free,), phi=(self.n_modes, p.sumdof), info=(), sweeps=())
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self.stage = []
+        for _ in range(n_streams):
+            d_in = {k: torch.empty((self.chunk,) + s, dtype=torch.float64, device=self.device)
+                    for k, s in self.in_shapes.items()}
+            d_out = {k: torch.empty((self.chunk,) + s, device=self.device,
+                                    dtype=torch.int32 if k in ('info', 'sweeps') else torch.float64)
+                     for k, s in self.out_shapes.items()}
+            self.stage.append((d_in, d_out))
+        self.launches = 0
+
+    def alloc_host(self, B: int):
+        """Pinned host input and output buffers for a batch of B."""
+        h_in = {k: torch.empty((B,) + s, dtype=torch.float64).pin_memory() for k, s in self.in_shapes.items()}
+        h_out = {k: torch.empty((B,) + s, dtype=torch.int32 if k in ('info', 'sweeps') else torch.float64).pin_memory()
+                 for k, s in self.out_shapes.items()}
+        return h_in, h_out
+
+    def bytes_per_structure(self):
+        import math
+        bi = sum(8 * math.prod(s) for s in self.in_shapes.values())
+        bo = sum((4 if k in ('info', 'sweeps') else 8) * math.prod(s) for k, s in self.out_shapes.items())
+        return bi, bo
+
+    def run(self, h_in: dict, h_out: dict):
+        """Enqueue the whole batch; returns after everything has landed in h_out."""
+        B = h_in['coords'].shape[0]
+        use_static = self.C > 0
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for ci, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(B, lo + self.chunk)
+            m = hi - lo
+            st = self.streams[ci % len(self.streams)]
+            d_in, d_out = self.stage[ci % len(self.streams)]
+            with torch.cuda.stream(st):
+                for k in self.IN_KEYS:
+                    if not use_static and k in ('f_nodal', 'r_local'):
+                        continue
+                    d_in[k][:m].copy_(h_in[k][lo:hi], non_blocking=True)
+                solve_fused(self.plan, d_in['coords'][:m], d_in['props'][:m], d_in['nodal_mass'][:m],
+                            d_in['f_nodal'][:m] if use_static else None,
+                            d_in['r_local'][:m] if use_static else None,
+                            modal=self.modal, n_modes=self.n_modes,
+                            out={k: v[:m] for k, v in d_out.items()})
+                self.launches += 1
+                for k in self.OUT_KEYS:
+                    if d_out[k].numel() == 0:
+                        continue
+                    if not use_static and k in ('u', 'endforces', 'reactions'):
+                        continue
+                    if not self.modal and k in ('lam', 'phi'):
+                        continue
+                    h_out[k][lo:hi].copy_(d_out[k][:m], non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return h_out

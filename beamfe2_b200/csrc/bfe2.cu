@@ -382,7 +382,8 @@ int bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int
     p->n = 0;
     for (int pos = 0; pos < p->sumdof; ++pos)
         if (p->free_of_pos[pos] == 0) { p->free_of_pos[pos] = p->n++; p->pos_of_free.push_back(pos); }
-    if (p->n == 0) { delete p; return fail(-1, "no free DOF left"); }
+    // n == 0 (every DOF supported, e.g. the clamped-clamped element of Tests/test_internal_beamloads.py)
+    // is legal for the static path: u = 0, end forces = -r_local.  The modal path is refused.
     // half bandwidth in free numbering
     p->hbw = 0;
     for (int e = 0; e < n_elem; ++e) {
@@ -424,7 +425,7 @@ int bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int
     p->lumped.assign(n_elem, 0);
     if (lumped) p->lumped.assign(lumped, lumped + n_elem);
     p->npad = p->n + (p->n & 1);
-    if (jacobi_config(p->n, &p->rpl, &p->lpp)) {
+    if (p->n > 0 && jacobi_config(p->n, &p->rpl, &p->lpp)) {
         p->LD = p->rpl * p->lpp;
         p->nthreads = std::max(64, ((p->npad / 2) * p->lpp + 31) / 32 * 32);
     } else {
@@ -500,8 +501,8 @@ int bfe2_element_km(int64_t nE, const double* xi, const double* yi, const double
 
 int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const double* props,
                          const double* nodal_mass, double* Kb, double* Mb, void* stream) {
+    if (plan && B == 0) return 0;
     if (!plan || B < 0 || !coords || !props || !Kb) return fail(-1, "bfe2_assemble_banded: bad argument");
-    if (B == 0) return 0;
     if (int r = plan_upload(plan)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
@@ -523,9 +524,9 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
 int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, const double* coords,
                       const double* props, const double* f_nodal, const double* r_local, double* u,
                       double* endforces, double* reactions, int32_t* info, void* stream) {
+    if (plan && B == 0) return 0;
     if (!plan || B < 0 || C < 1 || !Kb || !coords || !props || !f_nodal || !u || !info)
         return fail(-1, "bfe2_static_solve: bad argument");
-    if (B == 0) return 0;
     if (int r = plan_upload(plan)) return r;
     BatchArgs A{};
     A.B = B; A.C = C; A.do_static = 1; A.do_modal = 0; A.max_sweeps = BFE2_MAX_SWEEPS;
@@ -547,9 +548,10 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
 
 int bfe2_modal_solve(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Kb, const double* Mb,
                      double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream) {
+    if (plan && B == 0) return 0;
     if (!plan || B < 0 || !Kb || !Mb || !lam || !info) return fail(-1, "bfe2_modal_solve: bad argument");
     if (n_modes < 0 || n_modes > plan->n || (n_modes > 0 && !phi)) return fail(-1, "bad n_modes");
-    if (plan->rpl == 0) return fail(-3, "n_free = %d is beyond the Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
+    if (plan->rpl == 0) return fail(-3, "n_free = %d is outside the Jacobi path (1..%d)", plan->n, BFE2_MAX_JACOBI_N);
     if (B == 0) return 0;
     if (int r = plan_upload(plan)) return r;
     BatchArgs A{};
@@ -563,6 +565,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
                      const double* f_nodal, const double* r_local, double* u, double* endforces,
                      double* reactions, double* lam, double* phi, int32_t* info, int32_t* sweeps,
                      void* stream) {
+    if (plan && B == 0) return 0;
     if (!plan || B < 0 || C < 0 || !coords || !props || !info) return fail(-1, "bfe2_solve_fused: bad argument");
     if (C > 0 && (!f_nodal || !u)) return fail(-1, "static outputs requested without f_nodal / u");
     if (C == 0 && !do_modal) return fail(-1, "nothing to do");
@@ -570,7 +573,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         if (!lam) return fail(-1, "lam is NULL");
         if (n_modes < 0 || n_modes > plan->n || (n_modes > 0 && !phi)) return fail(-1, "bad n_modes");
         if (plan->rpl == 0)
-            return fail(-3, "n_free = %d is beyond the Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
+            return fail(-3, "n_free = %d is outside the Jacobi path (1..%d)", plan->n, BFE2_MAX_JACOBI_N);
     }
     if (B == 0) return 0;
     if (int r = plan_upload(plan)) return r;

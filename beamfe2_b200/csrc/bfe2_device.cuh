@@ -218,9 +218,13 @@ __device__ __forceinline__ void stage_assemble(const PlanDev& P, const double* s
 // In-place banded Cholesky by ONE WARP.  Ab[d*n + j] = A[j+d][j], d = 0..b.  Returns 0 or the
 // 1-based column of the first non-positive pivot (uniform across the warp).  Also writes 1/L[j][j].
 __device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, int n, int b, int lane) {
+    // invdiag[j] holds the ORIGINAL diagonal until column j is eliminated: a pivot that has lost all
+    // its digits (<= 64 eps * original) is reported as non-positive, i.e. numerically singular.
+    for (int j = lane; j < n; j += 32) invdiag[j] = Ab[j];
+    __syncwarp();
     for (int j = 0; j < n; ++j) {
         const double ajj = Ab[j];
-        if (!(ajj > 0.0) || !isfinite(ajj)) return j + 1;
+        if (!(ajj > 1.4210854715202004e-14 * invdiag[j]) || !isfinite(ajj)) return j + 1;
         const double ljj = sqrt(ajj);
         const double inv = 1.0 / ljj;
         const int m = min(b, n - 1 - j);

@@ -1,0 +1,347 @@
+"""GPU parity tests (-m gpu): every CUDA kernel, through the C ABI, against the CPU oracle, the
+golden vectors of the real reference and the 40-digit truth fixture.
+
+Tolerances (north_star): 1e-10 relative for displacements, eigenvalues and M-normalised modes (modes
+up to sign); integer maps bit-exact (tests/test_plan_abi.py).  Where scipy's own FP64 error exceeds
+1e-10 (small eigenvalues of a pencil with lam_max/lam_min ~ 1e7) the comparison with scipy uses
+LAPACK's error bound and the 1e-10 claim is checked against the 40-digit truth instead."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from beamfe2_b200 import batch, sweep
+from beamfe2_b200.plan import Plan
+from oracle import beamfe2_oracle as orc
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+EPS = np.finfo(float).eps
+
+
+def T(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
+
+
+def gpu_model(model, modal=True, n_modes=None, fused=True):
+    """One model dict through the GPU path as a batch of 1."""
+    pm = util.pack(model)
+    nN = len(model['nodes'])
+    plan = Plan.from_supports(nN, pm['conn'], model['supports'], pm['lumped'])
+    C = pm['f_nodal'].shape[0]
+    kw = dict(coords=T(pm['coords'][None]), props=T(pm['props'][None]), nodal_mass=T(pm['nodal_mass'][None]))
+    if C:
+        kw.update(f_nodal=T(pm['f_nodal'][None]), r_local=T(pm['r_local'][None]))
+    out = batch.solve_fused(plan, modal=modal and plan.n_free > 0, n_modes=n_modes, **kw)
+    torch.cuda.synchronize()
+    return plan, pm, {k: (v[0].cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+def p20_batch(B, shard=None):
+    P = sweep.p20_draw_params(B, shard)
+    pk = sweep.p20_pack(torch.from_numpy(P).to(DEV))
+    conn, sup = sweep.p20_topology()
+    plan = Plan.from_supports(21, conn, sup)
+    return P, pk, plan
+
+
+def oracle_p20(pk, n_modes=None):
+    conn, sup = sweep.p20_topology()
+    h = {k: v.cpu().numpy() for k, v in pk.items()}
+    return orc.solve_batch(conn, orc.positions_to_eliminate(sup), h['coords'], h['props'], h['nodal_mass'],
+                           h['f_nodal'], h['r_local'], n_modes=n_modes)
+
+
+# ------------------------------------------------------------------------------------------- K1
+def test_k1_element_known_answers():
+    """Tests/test_beam_linear_elastic.py:37-46 (unit beam integer matrix) and :140-151 (rotated)."""
+    one = T([1.0])
+    Kg, Mg = batch.element_km(T([0.]), T([0.]), one, T([0.]), one, one, one, one)
+    exp = np.array([[1, 0, 0, -1, 0, 0], [0, 12, 6, 0, -12, 6], [0, 6, 4, 0, -6, 2],
+                    [-1, 0, 0, 1, 0, 0], [0, -12, -6, 0, 12, -6], [0, 6, 2, 0, -6, 4]], dtype=float)
+    assert np.array_equal(Kg[0].cpu().numpy(), exp)
+    for case in ('rot_beam', 'vertical_beam', 'unit_beam'):
+        m = util.golden_models()[case]
+        g = util.golden(case)
+        (xi, yi), (xj, yj) = m['nodes']
+        b = m['beams'][0]
+        Kg, Mg = batch.element_km(T([xi]), T([yi]), T([xj]), T([yj]), T([b['E']]), T([b['A']]), T([b['I']]),
+                                  T([b['rho']]))
+        assert util.relmax(Kg.cpu().numpy(), g['Ke_global']) < 1e-14
+        assert util.relmax(Mg.cpu().numpy(), g['Me_global']) < 1e-14
+
+
+@pytest.mark.parametrize('nE', [1, 31, 32, 33, 10007, 300000])
+def test_k1_element_random(nE):
+    rng = np.random.default_rng(nE)
+    xi, yi = rng.uniform(-1e3, 1e3, nE), rng.uniform(-1e3, 1e3, nE)
+    ang = rng.uniform(-math.pi, math.pi, nE)
+    ang[: min(nE, 8)] = [0, math.pi / 2, -math.pi / 2, math.pi, math.atan(0.5), 1e-9, 3.0, -3.0][: min(nE, 8)]
+    L = rng.uniform(0.5, 5e3, nE)
+    xj, yj = xi + L * np.cos(ang), yi + L * np.sin(ang)
+    E, A = rng.uniform(1e4, 3e5, nE), rng.uniform(1, 1e5, nE)
+    I, rho = rng.uniform(1, 1e9, nE), rng.uniform(1e-9, 1e-8, nE)
+    lumped = (rng.uniform(size=nE) < 0.25)
+    Kg, Mg = batch.element_km(*(T(a) for a in (xi, yi, xj, yj, E, A, I, rho)), lumped=T(lumped, torch.uint8))
+    coords = np.stack([np.stack([xi, yi], -1), np.stack([xj, yj], -1)], axis=1)      # [nE, 2, 2]
+    props = np.stack([E, A, I, rho], -1)[:, None, :]
+    Ko, Mo = orc.element_km_global(coords, np.array([[0, 1]]), props, lumped[:, None])
+    Kg, Mg = Kg.cpu().numpy(), Mg.cpu().numpy()
+    ek = np.abs(Kg - Ko[:, 0]).max(axis=(1, 2)) / np.abs(Ko[:, 0]).max(axis=(1, 2))
+    em = np.abs(Mg - Mo[:, 0]).max(axis=(1, 2)) / np.abs(Mo[:, 0]).max(axis=(1, 2))
+    assert ek.max() < 1e-14 and em.max() < 1e-14       # relative to each matrix's largest entry
+    assert np.array_equal(Kg, np.swapaxes(Kg, 1, 2)) or util.relmax(Kg, np.swapaxes(Kg, 1, 2)) < 1e-15
+
+
+# ------------------------------------------------------------------------------------------- K2
+def test_k2_assembly_p20_vs_oracle():
+    P, pk, plan = p20_batch(512)
+    Kb, Mb = batch.assemble_banded(plan, pk['coords'], pk['props'], pk['nodal_mass'])
+    o = oracle_p20(pk)
+    Kd = plan.band_to_dense(Kb.cpu().numpy())
+    Md = plan.band_to_dense(Mb.cpu().numpy())
+    for b in range(512):
+        assert util.relmax(np.tril(Kd[b]), np.tril(o['Kc'][b])) < 1e-14
+        assert util.relmax(np.tril(Md[b]), np.tril(o['Mc'][b])) < 1e-14
+    Kb2, none = batch.assemble_banded(plan, pk['coords'], pk['props'], None, want_mass=False)
+    assert none is None and torch.equal(Kb, Kb2)
+
+
+@pytest.mark.parametrize('case', ['chopra_102', 'chopra_103', 'chopra_105', 'allresults_1_mass', 'allresults_2_mass',
+                                  'rod30_lumped', 'cantilever_example'])
+def test_k2_assembly_golden(case):
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    pm = util.pack(model)
+    plan = Plan.from_supports(len(model['nodes']), pm['conn'], model['supports'], pm['lumped'])
+    Kb, Mb = batch.assemble_banded(plan, T(pm['coords'][None]), T(pm['props'][None]), T(pm['nodal_mass'][None]))
+    Kc = orc.condense(g['K'], pm['fixed'])
+    Mc = orc.condense(g['M_with_masses'], pm['fixed'])
+    assert util.relmax(np.tril(plan.band_to_dense(Kb[0].cpu().numpy())), np.tril(Kc)) < 1e-14
+    assert util.relmax(np.tril(plan.band_to_dense(Mb[0].cpu().numpy())), np.tril(Mc)) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------- K3
+STATIC_CASES = ['unit_beam', 'rot_beam', 'vertical_beam', 'cantilever_example', 'chopra_105', 'allresults_1',
+                'allresults_2', 'allresults_4', 'three_elements', 'clamped_clamped_loads',
+                'p20_v0', 'p20_v1', 'p20_v2', 'p20_v3']
+
+
+@pytest.mark.parametrize('case', STATIC_CASES)
+def test_static_golden(case):
+    """Displacements, local end forces and reactions against what the REAL reference computed."""
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    plan, pm, out = gpu_model(model, modal=False)
+    assert out['info'] == 0
+    keep = plan.pos_of_free
+    fixed = plan.fixed
+    assert (out['u'][:, fixed] == 0).all()             # exact zeros at supports (reference: -R/1e41)
+    if len(keep):
+        o = orc.solve_batch(pm['conn'], pm['fixed'], pm['coords'], pm['props'], f_nodal=pm['f_nodal'],
+                            r_local=pm['r_local'])
+        assert util.relmax(out['u'], o['u']) < 1e-10                      # vs numpy.linalg.solve
+        assert util.relmax(out['u'][:, keep], g['u'][:, keep]) < 1e-9     # vs the reference's inv(K+1e41)
+    assert util.relmax(out['endforces'], g['endforces']) < 1e-9
+    assert util.relmax(out['reactions'], g['reactions']) < 1e-9
+
+
+def test_static_unfused_equals_fused_and_oracle():
+    P, pk, plan = p20_batch(300)
+    Kb, _ = batch.assemble_banded(plan, pk['coords'], pk['props'], None, want_mass=False)
+    s = batch.static_solve(plan, Kb, pk['coords'], pk['props'], pk['f_nodal'], pk['r_local'])
+    f = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], modal=False)
+    for k in ('u', 'endforces', 'reactions', 'info'):
+        assert torch.equal(s[k], f[k]), k
+    assert (s['info'] == 0).all()
+    o = oracle_p20(pk)
+    u = s['u'].cpu().numpy()
+    for b in range(300):
+        assert util.relmax(u[b], o['u'][b]) < 1e-10
+        assert util.relmax(s['endforces'][b].cpu().numpy(), o['endforces'][b]) < 1e-10
+        assert util.relmax(s['reactions'][b].cpu().numpy(), o['reactions'][b]) < 1e-10
+    t = util.p20_truth()                               # 40-digit solve of the same K, f
+    nt = t['u'].shape[0]
+    P, pk, plan = p20_batch(nt)                        # (the generator draws per-column [B] arrays)
+    assert np.array_equal(P, t['params'])
+    s = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], modal=False)
+    assert util.relmax(s['u'].cpu().numpy(), t['u']) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------- K4
+MODAL_CASES = ['unit_beam', 'cantilever_example', 'chopra_102', 'chopra_103', 'chopra_105', 'allresults_1',
+               'allresults_1_mass', 'allresults_2', 'allresults_2_mass', 'three_elements', 'rod30_consistent',
+               'p20_v0', 'p20_v1', 'p20_v2', 'p20_v3']
+
+
+@pytest.mark.parametrize('case', MODAL_CASES)
+def test_modal_golden(case):
+    """Circular frequencies and mode shapes against the REAL reference (scipy.linalg.eigh inside)."""
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    plan, pm, out = gpu_model(model)
+    assert out['info'] == 0 and 0 < out['sweeps'] < 30
+    lam = out['lam']
+    assert (np.diff(lam) >= 0).all()
+    w = np.sqrt(lam)
+    wr = g['circular_freq']
+    bound = 1e-10 + 64 * EPS * (wr[-1] / wr) ** 2
+    assert (np.abs(w / wr - 1) < bound).all()
+    # shapes: zeros at supports, M-orthonormal, eigen-residual; per-mode match where the gap allows
+    phi = out['phi']
+    assert (phi[:, plan.fixed] == 0).all()
+    Mc = orc.condense(g['M_with_masses'], pm['fixed'])
+    Kc = orc.condense(g['K'], pm['fixed'])
+    Pf = phi[:, plan.pos_of_free]
+    assert np.abs(Pf @ Mc @ Pf.T - np.eye(len(lam))).max() < 1e-9
+    res = Kc @ Pf.T - (Mc @ Pf.T) * lam[None, :]
+    assert (np.abs(res).max(axis=0) / (np.abs(Kc).max() * np.abs(Pf).max(axis=1))).max() < 1e-11
+    gap = np.minimum(np.diff(lam, prepend=-np.inf), np.diff(lam, append=np.inf))
+    tol = 1e-10 + 256 * EPS * lam[-1] / gap
+    assert (util.mode_err(phi, g['shapes']) < tol).all()
+
+
+def test_modal_p20_truth_1e10():
+    """The north_star bar, against a 40-digit solution of the same pencils: eigenvalues and the first
+    10 M-normalised modes to 1e-10 relative."""
+    t = util.p20_truth()
+    nt = t['lam'].shape[0]
+    P, pk, plan = p20_batch(nt)
+    assert np.array_equal(P, t['params'])
+    out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
+                            n_modes=10)
+    assert (out['info'] == 0).all()
+    lam = out['lam'].cpu().numpy()
+    phi = out['phi'].cpu().numpy()
+    assert np.abs(lam / t['lam'] - 1).max() < 1e-10
+    assert util.mode_err(phi, t['phi']).max() < 1e-10
+    # sign convention: the largest-magnitude entry of every mode is positive
+    big = np.take_along_axis(phi, np.abs(phi).argmax(axis=-1)[..., None], axis=-1)
+    assert (big > 0).all()
+
+
+def test_modal_p20_vs_scipy_batch():
+    B = 400
+    P, pk, plan = p20_batch(B, shard=3)
+    out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], None, None, n_modes=10)
+    assert (out['info'] == 0).all()
+    sw = out['sweeps'].cpu().numpy()
+    assert sw.min() >= 5 and sw.max() <= 16
+    o = oracle_p20(pk, n_modes=10)
+    lam = out['lam'].cpu().numpy()
+    bound = 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']            # scipy's own (LAPACK) error bound
+    assert (np.abs(lam / o['lam'] - 1) < bound).all()
+    # Rayleigh quotients of scipy's vectors in extended precision are second-order accurate: a much
+    # tighter reference for the eigenvalues than scipy's eigenvalues themselves
+    Kc, Mc = o['Kc'].astype(np.longdouble), o['Mc'].astype(np.longdouble)
+    keep = plan.pos_of_free
+    V = o['phi'][:, :, keep].astype(np.longdouble)
+    rq = np.einsum('bmi,bij,bmj->bm', V, Kc, V) / np.einsum('bmi,bij,bmj->bm', V, Mc, V)
+    assert np.abs(lam[:, :10] / rq.astype(np.float64) - 1).max() < 1e-10
+    gap = np.minimum(np.diff(o['lam'], axis=1, prepend=-np.inf), np.diff(o['lam'], axis=1, append=np.inf))[:, :10]
+    tol = 1e-10 + 256 * EPS * o['lam'][:, -1:] / gap
+    assert (util.mode_err(out['phi'].cpu().numpy(), o['phi']) < tol).all()
+
+
+def test_modal_unfused_equals_fused():
+    P, pk, plan = p20_batch(200)
+    Kb, Mb = batch.assemble_banded(plan, pk['coords'], pk['props'], pk['nodal_mass'])
+    m = batch.modal_solve(plan, Kb, Mb, n_modes=10)
+    f = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'], n_modes=10)
+    for k in ('lam', 'phi', 'info', 'sweeps'):
+        assert torch.equal(m[k], f[k]), k
+
+
+def test_rod30_analytic_and_lumped():
+    """Tests/test_beam_modal.py:61-84 -- first five omegas within 1 % of [3.52, 22.03, 61.7, 121, 200] *
+    sqrt(EI / rho A L^4), consistent and lumped mass (n_free = 90: the 4-lanes-per-pair Jacobi path)."""
+    E, rho, L = 2.1e11, 7850, 0.45
+    A, I = 0.003 * 0.02, 0.02 * 0.003 ** 3 / 12
+    ana = np.array([3.52, 22.03, 61.7, 121, 200]) * math.sqrt(E * I / (rho * A * L ** 4))
+    for case in ('rod30_consistent', 'rod30_lumped'):
+        plan, pm, out = gpu_model(util.golden_models()[case], n_modes=12)
+        assert plan.n_free == 90 and out['info'] == 0
+        w = np.sqrt(out['lam'])
+        bending = [x for x in w if x < 0.9 * math.sqrt(E / rho) * math.pi / (2 * L)][:5]   # below 1st axial
+        assert np.abs(np.array(bending) / ana - 1).max() < 0.01, case
+
+
+# ------------------------------------------------------------------------------------------- edges
+def test_failure_reporting_and_edge_cases():
+    conn, sup = sweep.p20_topology()
+    P, pk, plan = p20_batch(8)
+    # (a) K not positive definite -> info = 1-based column of the bad pivot, NaN outputs.  A free-free
+    #     structure is singular only up to rounding, so the robust trigger is a negative modulus;
+    #     for the free-free case flagged variants must be NaN and unflagged ones finite.
+    neg = pk['props'].clone()
+    neg[..., 0] = -neg[..., 0]
+    out = batch.solve_fused(plan, pk['coords'], neg, pk['nodal_mass'], pk['f_nodal'], pk['r_local'], modal=False)
+    assert (out['info'] == 1).all() and torch.isnan(out['u']).all() and torch.isnan(out['reactions']).all()
+    free_plan = Plan(21, conn, [])
+    out = batch.solve_fused(free_plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
+                            modal=False)
+    bad = out['info'] > 0
+    assert bad.sum() >= 6                        # the relative pivot test catches (almost) all of them
+    assert torch.isnan(out['u'][bad]).all() and torch.isfinite(out['u'][~bad]).all()
+    # (b) massless structure: M not positive definite -> info = -1 (reference returns False, Solver.py:34-35)
+    props0 = pk['props'].clone()
+    props0[..., 3] = 0.0
+    out = batch.solve_fused(plan, pk['coords'], props0, None, None, None, n_modes=3)
+    assert (out['info'] == -1).all() and torch.isnan(out['lam']).all()
+    # (c) one bad variant does not disturb its neighbours
+    props1 = pk['props'].clone()
+    props1[3, :, 3] = 0.0
+    out = batch.solve_fused(plan, pk['coords'], props1, None, pk['f_nodal'], pk['r_local'], n_modes=2)
+    good = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], n_modes=2)
+    info = out['info'].cpu().numpy()
+    assert info[3] == -1 and (np.delete(info, 3) == 0).all()
+    keepers = [b for b in range(8) if b != 3]
+    assert torch.equal(out['lam'][keepers], good['lam'][keepers])
+    assert torch.equal(out['u'][keepers], good['u'][keepers])
+    # (d) empty batch and wrong shapes
+    e = batch.solve_fused(plan, pk['coords'][:0], pk['props'][:0], None, None, None, n_modes=0)
+    assert e['lam'].shape == (0, 57)
+    with pytest.raises(Exception):
+        batch.solve_fused(plan, pk['coords'][:, :5], pk['props'], None, None, None)
+    with pytest.raises(Exception):
+        batch.solve_fused(plan, pk['coords'].cpu(), pk['props'].cpu(), None, None, None)
+
+
+def test_large_batch_properties():
+    """Config-3 size (1e5 variants): properties that need no CPU solve -- info, ordering, K u = f via the
+    reactions at free DOFs (sum of end forces minus loads must vanish), M-orthonormality, eigen-residual."""
+    B = 100000
+    P, pk, plan = p20_batch(B)
+    out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'], n_modes=10)
+    torch.cuda.synchronize()
+    assert (out['info'] == 0).all()
+    lam = out['lam']
+    assert (lam[:, 1:] >= lam[:, :-1]).all() and (lam > 0).all()
+    free = torch.as_tensor(plan.pos_of_free.astype(np.int64), device=DEV)
+    react = out['reactions']
+    scale = react.abs().amax(dim=(1, 2), keepdim=True)
+    assert (react[:, :, free].abs() / scale).max() < 1e-9            # equilibrium at every free DOF
+    # global equilibrium: support reactions balance the applied loads (FX, FY per load case)
+    conn, sup = sweep.p20_topology()
+    Kb, Mb = batch.assemble_banded(plan, pk['coords'], pk['props'], pk['nodal_mass'])
+    n, hb = plan.n_free, plan.hbw
+    sub = slice(0, 4096)
+    Md = torch.zeros((4096, n, n), dtype=torch.float64, device=DEV)
+    Kd = torch.zeros_like(Md)
+    for d in range(hb + 1):
+        idx = torch.arange(n - d, device=DEV)
+        Md[:, idx + d, idx] = Mb[sub, d, : n - d]
+        Md[:, idx, idx + d] = Mb[sub, d, : n - d]
+        Kd[:, idx + d, idx] = Kb[sub, d, : n - d]
+        Kd[:, idx, idx + d] = Kb[sub, d, : n - d]
+    Pf = out['phi'][sub][:, :, free]
+    G = Pf @ Md @ Pf.transpose(1, 2)
+    assert (G - torch.eye(10, dtype=torch.float64, device=DEV)).abs().max() < 1e-10
+    R = Kd @ Pf.transpose(1, 2) - (Md @ Pf.transpose(1, 2)) * lam[sub, None, :10]
+    rel = R.abs().amax(dim=1) / (Kd.abs().amax(dim=(1, 2))[:, None] * Pf.abs().amax(dim=2))
+    assert rel.max() < 1e-12
+    # trace identity: sum of all eigenvalues == trace(M^-1 K)
+    tr = torch.linalg.solve(Md, Kd).diagonal(dim1=1, dim2=2).sum(dim=1)
+    assert ((lam[sub].sum(dim=1) / tr) - 1).abs().max() < 1e-10
