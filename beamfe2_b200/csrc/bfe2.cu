@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,7 +85,7 @@ int plan_upload(bfe2_plan* p) {
     const int32_t* base = static_cast<const int32_t*>(p->d_blob);
     PlanDev& d = p->dev;
     d.nN = p->nN; d.nE = p->nE; d.sumdof = p->sumdof; d.n = p->n; d.hbw = p->hbw; d.nslots = p->nslots;
-    d.npad = p->npad; d.LD = p->LD;
+    d.npad = p->npad; d.LD = p->LD; d.off = p->npad - p->n;
     d.conn = base + off[0];
     d.free_of_pos = base + off[1];
     d.pos_of_free = base + off[2];
@@ -219,7 +220,7 @@ k_assemble(PlanDev P, BatchArgs A) {
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
 //   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
 //   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE>
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
 __global__ void __launch_bounds__(NT, MINB)
 k_solve(PlanDev P, BatchArgs A) {
     extern __shared__ __align__(16) double smem[];
@@ -296,7 +297,9 @@ k_solve(PlanDev P, BatchArgs A) {
     if (A.do_modal) {
         double* s_W = smem + L.U;
         stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
-        const int sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
+        int sw;
+        if constexpr (REGS) sw = stage_jacobi_regs<RPL>(P, s_W, A.max_sweeps, tid);
+        else sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
         if (sw < 0) info = -2;
         if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
         stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,
@@ -307,25 +310,35 @@ k_solve(PlanDev P, BatchArgs A) {
     if (tid == 0) A.info[b] = info;
 }
 
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE>
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
 int launch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
+    PlanDev P = plan->dev;
+    P.off = REGS ? 0 : plan->npad - plan->n;
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
-    auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE>;
+    auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE, REGS>;
     BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     if (A.B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
-    kern<<<(unsigned)A.B, NT, bytes, stream>>>(plan->dev, A);
+    kern<<<(unsigned)A.B, NT, bytes, stream>>>(P, A);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <bool ASSEMBLE>
 int dispatch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
-    if (plan->rpl == 5 && plan->lpp == 2) return launch_solve<5, 2, 64, 8, ASSEMBLE>(plan, A, stream);
-    if (plan->rpl == 15 && plan->lpp == 2) return launch_solve<15, 2, 64, 8, ASSEMBLE>(plan, A, stream);
-    if (plan->rpl == 29 && plan->lpp == 2) return launch_solve<29, 2, 64, 6, ASSEMBLE>(plan, A, stream);
-    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE>(plan, A, stream);
+    // n <= 58: register-resident odd-even Jacobi (two warps per structure); BFE2_JACOBI=smem selects the
+    // shared-memory round-robin variant for A/B measurements.  58 < n <= 116: shared-memory variant.
+    static const bool use_smem = [] { const char* e = getenv("BFE2_JACOBI"); return e && !strcmp(e, "smem"); }();
+    if (plan->lpp == 2 && !use_smem) {
+        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
+        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
+        if (plan->rpl == 29) return launch_solve<29, 2, 64, 6, ASSEMBLE, true>(plan, A, stream);
+    }
+    if (plan->rpl == 5 && plan->lpp == 2) return launch_solve<5, 2, 64, 8, ASSEMBLE, false>(plan, A, stream);
+    if (plan->rpl == 15 && plan->lpp == 2) return launch_solve<15, 2, 64, 8, ASSEMBLE, false>(plan, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 2) return launch_solve<29, 2, 64, 6, ASSEMBLE, false>(plan, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
 
@@ -538,7 +551,7 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
-    auto kern = k_solve<5, 2, 64, 8, false>;
+    auto kern = k_solve<5, 2, 64, 8, false, false>;
     BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
     kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
@@ -589,7 +602,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
         const size_t bytes = (size_t)L.total * sizeof(double);
         if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
-        auto kern = k_solve<5, 2, 64, 8, true>;
+        auto kern = k_solve<5, 2, 64, 8, true, false>;
         BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
         kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);

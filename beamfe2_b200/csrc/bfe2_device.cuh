@@ -17,6 +17,7 @@ struct PlanDev {
     int nN, nE, sumdof, n, hbw;   // nodes, beams, 3*nN, free DOFs, half bandwidth (free numbering)
     int nslots;                   // (hbw+1)*n band slots
     int npad, LD;                 // Jacobi: even slot count >= n, leading dimension (rows, padded)
+    int off;                      // slot of row 0 of G: npad-n (dummy column in slot 0, v1) or 0 (dummy last, v2)
     const int32_t* conn;          // [nE*2]
     const int32_t* free_of_pos;   // [sumdof]
     const int32_t* pos_of_free;   // [n]
@@ -50,7 +51,7 @@ __host__ __device__ inline SmemLayout make_layout(int nN, int nE, int n, int hbw
     L.invM = o;   o += n;
     o = (o + 1) & ~1;                                   // 16-byte align the big region
     L.U = o;
-    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), npad * LD);
+    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 256) ? 256 : npad * LD);
     L.lam = o;    o += npad;
     L.order = o;  o += (npad + 1) / 2 + 1;              // npad int32 + 2 flags, stored in double slots
     L.total = o;
@@ -445,11 +446,130 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
     return converged ? sweeps : -sweeps;           // negative: not converged within max_sweeps
 }
 
-// Form W = G^T in the slot layout:  slot (k + off) holds row k of G = Lm^-1 Lk, off = npad - n.
+// ------------------------------------------------------------------------------------------------
+// Stage M, register-resident variant (n <= 58): the same one-sided Jacobi, but the columns never
+// leave the register file during the sweeps.
+//
+//   Layout: TWO warps per structure; warp h owns rows [h*RPL, (h+1)*RPL) of EVERY column, lane k owns
+//   the columns at line positions 2k (A) and 2k+1 (B).  Ordering: odd-even transposition on a line of
+//   npad (even) positions -- step s pairs positions (i, i+1), i = s mod 2, rotates them and
+//   interchanges them; after npad steps every pair has met exactly once.  With the interchange folded
+//   into the neighbour exchange the per-step data movement is ONE cyclic warp shuffle of one column:
+//       even step: rotate (A, B) in place;  B <- B of lane k+1 (cyclic)
+//       odd  step: rotate (A, B) in place;  A <- A of lane k-1 (cyclic);  the last lane, which holds
+//                  the two idle end positions, exchanges them ("rotation" c = 0, s = -1)
+//   Column norms travel with the columns and are updated by a' = a - t g, b' = b + t g (refreshed from
+//   the data at the start of every sweep), so a step costs one dot product, not three.  The two
+//   row-halves of the dot product meet through 2 x 8 bytes of shared memory per lane and one
+//   __syncthreads per step; both warps then compute bit-identical rotation parameters.
+// ------------------------------------------------------------------------------------------------
+template <int RPL>
+__device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
+    const int lane = tid & 31, h = tid >> 5;
+    const int npad = P.npad, LD = P.LD, NP = npad >> 1;
+    const bool act = lane < NP;
+    const int src_dn = act ? (lane + 1 == NP ? 0 : lane + 1) : lane;
+    const int src_up = act ? (lane == 0 ? NP - 1 : lane - 1) : lane;
+    double A[RPL], B[RPL];
+    {
+        const double* pa = s_W + (2 * lane) * LD + h * RPL;
+        const double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            A[r] = act ? pa[r] : 0.0;
+            B[r] = act ? pb[r] : 0.0;
+        }
+    }
+    __syncthreads();                                  // W is in registers: its memory becomes scratch
+    double* part_g = s_W;                             // [2 parity][2 warps][32 lanes]
+    double* part_n = s_W + 128;                       // [2 warps][32 lanes][2]
+    int sweeps = 0;
+    bool converged = false;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        // refresh the cached squared norms from the data
+        double nA, nB;
+        {
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+            for (int r = 0; r + 1 < RPL; r += 2) {
+                a0 = fma(A[r], A[r], a0); a1 = fma(A[r + 1], A[r + 1], a1);
+                b0 = fma(B[r], B[r], b0); b1 = fma(B[r + 1], B[r + 1], b1);
+            }
+            if (RPL & 1) { a0 = fma(A[RPL - 1], A[RPL - 1], a0); b0 = fma(B[RPL - 1], B[RPL - 1], b0); }
+            part_n[(h * 32 + lane) * 2] = a0 + a1;
+            part_n[(h * 32 + lane) * 2 + 1] = b0 + b1;
+            __syncthreads();
+            nA = part_n[lane * 2] + part_n[(32 + lane) * 2];
+            nB = part_n[lane * 2 + 1] + part_n[(32 + lane) * 2 + 1];
+        }
+        int rotated = 0;
+        for (int step = 0; step < npad; ++step) {
+            const int odd = step & 1;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+            for (int r = 0; r + 3 < RPL; r += 4) {
+                g0 = fma(A[r], B[r], g0); g1 = fma(A[r + 1], B[r + 1], g1);
+                g2 = fma(A[r + 2], B[r + 2], g2); g3 = fma(A[r + 3], B[r + 3], g3);
+            }
+#pragma unroll
+            for (int r = RPL & ~3; r < RPL; ++r) g0 = fma(A[r], B[r], g0);
+            double* pg = part_g + odd * 64;
+            pg[h * 32 + lane] = (g0 + g1) + (g2 + g3);
+            __syncthreads();
+            const double g = pg[lane] + pg[32 + lane];
+            const bool idle = odd && (lane == NP - 1);
+            double c = 1.0, s = 0.0;
+            bool upd = false;
+            if (act && !idle && fabs(g) > BFE2_JACOBI_TOL * sqrt(nA * nB)) {
+                const double zeta = (nB - nA) / (2.0 * g);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                c = 1.0 / sqrt(1.0 + t * t);
+                s = c * t;
+                nA -= t * g;
+                nB += t * g;
+                rotated = 1;
+                upd = true;
+            } else if (act && idle) {                 // exchange the two idle end columns (sign flip is
+                c = 0.0; s = -1.0;                    // immaterial: columns are defined up to sign)
+                const double tmp = nA; nA = nB; nB = tmp;
+                upd = true;
+            }
+            if (__any_sync(0xffffffffu, upd)) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    const double ar = A[r], br = B[r];
+                    A[r] = c * ar - s * br;
+                    B[r] = s * ar + c * br;
+                }
+            }
+            if (!odd) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) B[r] = __shfl_sync(0xffffffffu, B[r], src_dn);
+                nB = __shfl_sync(0xffffffffu, nB, src_dn);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) A[r] = __shfl_sync(0xffffffffu, A[r], src_up);
+                nA = __shfl_sync(0xffffffffu, nA, src_up);
+            }
+        }
+        if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
+    }
+    __syncthreads();                                  // scratch no longer read: W comes back
+    if (act) {
+        double* pa = s_W + (2 * lane) * LD + h * RPL;
+        double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) { pa[r] = A[r]; pb[r] = B[r]; }
+    }
+    __syncthreads();
+    return converged ? sweeps : -sweeps;
+}
+
+// Form W = G^T in the slot layout:  slot (k + off) holds row k of G = Lm^-1 Lk, off = P.off.
 // Thread j owns column j of G (forward substitution with the band factor Lm).
 __device__ __forceinline__ void stage_form_gt(const PlanDev& P, const double* s_Kb, const double* s_Mb,
                                               const double* s_invM, double* s_W, int tid, int nt) {
-    const int n = P.n, b = P.hbw, LD = P.LD, off = P.npad - P.n;
+    const int n = P.n, b = P.hbw, LD = P.LD, off = P.off;
     for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
     __syncthreads();
     for (int j = tid; j < n; j += nt) {
@@ -474,7 +594,7 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
         double acc = 0.0;
         const double* w = s_W + s * LD;
         for (int r = 0; r < n; ++r) acc = fma(w[r], w[r], acc);
-        s_lam[s] = (npad != n && s == 0) ? INFINITY : acc;
+        s_lam[s] = (npad != n && acc == 0.0) ? INFINITY : acc;   // the zero dummy column (n odd) sorts last
     }
     __syncthreads();
     for (int s = tid; s < npad; s += nt) {
