@@ -463,11 +463,85 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
 //   row-halves of the dot product meet through 2 x 8 bytes of shared memory per lane and one
 //   __syncthreads per step; both warps then compute bit-identical rotation parameters.
 // ------------------------------------------------------------------------------------------------
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) and
+// two Newton steps.  Arguments here are finite, normal and positive-or-signed (rcp) -- no special cases.
+__device__ __forceinline__ double rcp_fast(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
+template <int RPL, bool ODD>
+__device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
+                                                 int& rotated, double* pg, int h, int lane, bool act, bool last,
+                                                 int src) {
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+    for (int r = 0; r + 3 < RPL; r += 4) {
+        g0 = fma(A[r], B[r], g0); g1 = fma(A[r + 1], B[r + 1], g1);
+        g2 = fma(A[r + 2], B[r + 2], g2); g3 = fma(A[r + 3], B[r + 3], g3);
+    }
+#pragma unroll
+    for (int r = RPL & ~3; r < RPL; ++r) g0 = fma(A[r], B[r], g0);
+    pg[h * 32 + lane] = (g0 + g1) + (g2 + g3);
+    __syncthreads();
+    const double g = pg[lane] + pg[32 + lane];
+    // rotate when |g| > tol * sqrt(nA nB)  <=>  g^2 > tol^2 nA nB
+    const bool rot = act && !(ODD && last) && (g * g > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * (nA * nB));
+    double c = 1.0, s = 0.0;
+    if (ODD && last && act) {                         // exchange the two idle end columns (the sign flip is
+        c = 0.0; s = -1.0;                            // immaterial: columns are defined up to sign)
+        const double tmp = nA; nA = nB; nB = tmp;
+    }
+    if (rot) {
+        // tan(2 theta) = 2g / (nB - nA);  t = tan(theta) is the smaller root:  t = h / (d + sign(d) sqrt(d^2+h^2))
+        const double d = nB - nA, hh = 2.0 * g;
+        const double q = fma(d, d, hh * hh);
+        const double rq = q * rsqrt_fast(q);                       // sqrt(d^2 + h^2)
+        const double t = hh * rcp_fast(d + copysign(rq, d));
+        c = rsqrt_fast(fma(t, t, 1.0));
+        s = c * t;
+        nA = fma(-t, g, nA);
+        nB = fma(t, g, nB);
+        rotated = 1;
+    }
+    if (__any_sync(0xffffffffu, rot || (ODD && last && act))) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const double sb = s * B[r], cb = c * B[r];
+            B[r] = fma(s, A[r], cb);
+            A[r] = fma(c, A[r], -sb);
+        }
+    }
+    if (!ODD) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) B[r] = __shfl_sync(0xffffffffu, B[r], src);
+        nB = __shfl_sync(0xffffffffu, nB, src);
+    } else {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) A[r] = __shfl_sync(0xffffffffu, A[r], src);
+        nA = __shfl_sync(0xffffffffu, nA, src);
+    }
+}
+
 template <int RPL>
 __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
     const int lane = tid & 31, h = tid >> 5;
     const int npad = P.npad, LD = P.LD, NP = npad >> 1;
     const bool act = lane < NP;
+    const bool last = lane == NP - 1;
     const int src_dn = act ? (lane + 1 == NP ? 0 : lane + 1) : lane;
     const int src_up = act ? (lane == 0 ? NP - 1 : lane - 1) : lane;
     double A[RPL], B[RPL];
@@ -503,54 +577,9 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
             nB = part_n[lane * 2 + 1] + part_n[(32 + lane) * 2 + 1];
         }
         int rotated = 0;
-        for (int step = 0; step < npad; ++step) {
-            const int odd = step & 1;
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-#pragma unroll
-            for (int r = 0; r + 3 < RPL; r += 4) {
-                g0 = fma(A[r], B[r], g0); g1 = fma(A[r + 1], B[r + 1], g1);
-                g2 = fma(A[r + 2], B[r + 2], g2); g3 = fma(A[r + 3], B[r + 3], g3);
-            }
-#pragma unroll
-            for (int r = RPL & ~3; r < RPL; ++r) g0 = fma(A[r], B[r], g0);
-            double* pg = part_g + odd * 64;
-            pg[h * 32 + lane] = (g0 + g1) + (g2 + g3);
-            __syncthreads();
-            const double g = pg[lane] + pg[32 + lane];
-            const bool idle = odd && (lane == NP - 1);
-            double c = 1.0, s = 0.0;
-            bool upd = false;
-            if (act && !idle && fabs(g) > BFE2_JACOBI_TOL * sqrt(nA * nB)) {
-                const double zeta = (nB - nA) / (2.0 * g);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                c = 1.0 / sqrt(1.0 + t * t);
-                s = c * t;
-                nA -= t * g;
-                nB += t * g;
-                rotated = 1;
-                upd = true;
-            } else if (act && idle) {                 // exchange the two idle end columns (sign flip is
-                c = 0.0; s = -1.0;                    // immaterial: columns are defined up to sign)
-                const double tmp = nA; nA = nB; nB = tmp;
-                upd = true;
-            }
-            if (__any_sync(0xffffffffu, upd)) {
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    const double ar = A[r], br = B[r];
-                    A[r] = c * ar - s * br;
-                    B[r] = s * ar + c * br;
-                }
-            }
-            if (!odd) {
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) B[r] = __shfl_sync(0xffffffffu, B[r], src_dn);
-                nB = __shfl_sync(0xffffffffu, nB, src_dn);
-            } else {
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) A[r] = __shfl_sync(0xffffffffu, A[r], src_up);
-                nA = __shfl_sync(0xffffffffu, nA, src_up);
-            }
+        for (int step = 0; step < npad; step += 2) {
+            jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, part_g, h, lane, act, last, src_dn);
+            jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, part_g + 64, h, lane, act, last, src_up);
         }
         if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
     }
