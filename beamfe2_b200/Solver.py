@@ -1,0 +1,81 @@
+"""Solver operators of the drop-in API: same contract as the reference's BeamFE2/Solver.py:16-87 --
+`Solver(structure).solve() -> bool` reads the Structure and writes structure.results[...] -- but the
+arithmetic is the fused CUDA kernel of libbfe2 (batch of one).  There is no CPU fallback: without a
+CUDA device solve() raises."""
+import math
+
+import numpy as np
+
+from . import Results
+
+
+class Solver(object):
+    def __init__(self, structure=None):
+        self.structure = structure
+
+    def solve(self):
+        raise NotImplementedError
+
+
+def _run(structure, static, modal):
+    import torch
+    from . import batch
+    if not torch.cuda.is_available():
+        raise RuntimeError('beamfe2_b200 solvers need a CUDA device (no CPU fallback)')
+    plan, pk = structure.pack()
+
+    def dev(a):
+        return torch.as_tensor(np.ascontiguousarray(a[None]), dtype=torch.float64, device='cuda')
+    kw = dict(coords=dev(pk['coords']), props=dev(pk['props']))
+    if static:
+        kw.update(f_nodal=dev(pk['f_nodal']), r_local=dev(pk['r_local']))
+    if modal:
+        kw.update(nodal_mass=dev(pk['nodal_mass']))
+    out = batch.solve_fused(plan, modal=modal, n_modes=plan.n_free if modal else 0, **kw)
+    torch.cuda.synchronize()
+    return plan, {k: (v[0].cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+class LinearStaticSolver(Solver):
+    def solve(self):
+        st = self.structure
+        if st._load_vector is None or np.count_nonzero(st._load_vector) == 0:     # Solver.py:79-80
+            return False
+        plan, out = _run(st, static=True, modal=False)
+        if int(out['info']) != 0:
+            raise np.linalg.LinAlgError('stiffness matrix is singular (pivot %d)' % int(out['info']))
+        disps = np.matrix(out['u'][0]).T                                        # sumdof x 1, zeros at supports
+        st.results['linear static'] = Results.LinearStaticResult(structure=st, displacements=[disps],
+                                                                 endforces=out['endforces'][0],
+                                                                 reactions=out['reactions'][0])
+        st.results['linear static'].solved = True
+        return True
+
+
+class ModalSolver(Solver):
+    def solve(self):
+        st = self.structure
+        plan, pk = st.pack()
+        if plan.n_free == 0:
+            return False
+        if np.count_nonzero(pk['props'][:, 3] * pk['props'][:, 1]) == 0 and np.count_nonzero(pk['nodal_mass']) == 0:
+            return False                                                        # all-zero mass, Solver.py:34-35
+        plan, out = _run(st, static=False, modal=True)
+        info = int(out['info'])
+        if info == -1:
+            return False
+        if info != 0:
+            raise np.linalg.LinAlgError('modal solve failed (info %d)' % info)
+        lam = out['lam']
+        circfreq = [math.sqrt(x) for x in lam if x > 0]                         # Solver.py:42
+        shapes = [np.matrix(out['phi'][k]).T for k in range(out['phi'].shape[0])]
+        st.results['modal'] = Results.ModalResult(structure=st, circular_freq=circfreq, modalshapes=shapes)
+        st.results['modal'].solved = True
+        return True
+
+
+class BucklingSolver(Solver):
+    """Out of scope: the reference's buckling solver is unfinished (Solver.py:95-180 calls exit())."""
+
+    def solve(self):
+        raise NotImplementedError('linear buckling is not part of the accelerated path')

@@ -281,7 +281,7 @@ def run_gpu_arm(args):
     tj = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get('fused_bytes_per_launch')
+            traffic = json.load(open(tj)).get('fused_bytes_per_structure') * B
         except Exception:
             traffic = None
     line = {

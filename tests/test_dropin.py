@@ -1,0 +1,248 @@
+"""Drop-in Structure / Solver / Results API: host bookkeeping on the CPU, and (gpu) the reference's own
+test scenarios re-run through the GPU solvers with the reference's assertions and tolerances
+(Tests/__init__.py: ATOL = 1e-12)."""
+import math
+
+import numpy as np
+import pytest
+
+from beamfe2_b200 import HermitianBeam_2D as HB
+from beamfe2_b200 import Node, Structure, Loads
+from oracle import ref_harness as rh
+from tests import util
+
+ATOL = 1e-12
+
+
+def build(model):
+    nodes = [Node.Node(ID=k + 1, coords=c) for k, c in enumerate(model['nodes'])]
+    beams = [HB.HermitianBeam2D(ID=k + 1, i=nodes[b['i'] - 1], j=nodes[b['j'] - 1], E=b['E'], I=b['I'], A=b['A'],
+                                rho=b['rho']) for k, b in enumerate(model['beams'])]
+    for bm, b in zip(beams, model['beams']):
+        if b.get('lumped'):
+            bm.mass_matrix = 'lumped'
+    s = Structure.Structure(beams=beams, supports=model['supports'])
+    for nid, mass in model.get('masses', []):
+        s.add_nodal_mass(nodeID=nid, mass=dict(mass))
+    return s
+
+
+def apply(s, lc):
+    s.clear_loads()
+    for nid, dyn in lc.get('nodal', []):
+        s.add_nodal_load(nodeID=nid, dynam=dict(dyn))
+    for bi, kind, kw in lc.get('beam', []):
+        s.add_internal_loads(beam=s.beams[bi], loadtype=kind, **kw)
+
+
+# ------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize('case', ['allresults_1_mass', 'allresults_2', 'allresults_4', 'chopra_105', 'p20_v1',
+                                  'vertical_beam', 'clamped_clamped_loads'])
+def test_host_bookkeeping_matches_reference(case):
+    """Load vector, positions and packed tensors equal what the real reference produced (golden)."""
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    s = build(model)
+    assert s.sumdof == int(g['sumdof'])
+    assert s.positions_to_eliminate == g['positions_to_eliminate'].tolist()
+    pm = rh.pack_model(model)
+    for c, lc in enumerate(model.get('load_cases', [])):
+        apply(s, lc)
+        assert np.array_equal(np.asarray(s.load_vector).ravel(), g['f'][c])         # bit-exact
+        plan, pk = s.pack()
+        assert np.array_equal(pk['f_nodal'][0], pm['f_nodal'][c])
+        assert np.array_equal(pk['r_local'][0], pm['r_local'][c])
+    plan, pk = s.pack()
+    for k in ('coords', 'props', 'nodal_mass'):
+        assert np.array_equal(pk[k], pm[k])
+    assert np.array_equal(plan.fixed, g['positions_to_eliminate'].astype(np.int32))
+
+
+def test_api_surface_and_error_behaviour():
+    n1, n2 = Node.Node.from_dict({'ID': 1, 'coords': (0, 0)}), Node.Node(ID=2, coords=(3.0, 4.0))
+    with pytest.raises(Exception):
+        Node.Node.from_dict({'ID': 1})
+    b = HB.HermitianBeam2D.from_dict({'ID': 1, 'i': n1, 'j': n2, 'E': 10., 'I': 2., 'A': 3., 'rho': 1.})
+    with pytest.raises(Exception):
+        HB.HermitianBeam2D.from_dict({'ID': 1, 'i': n1, 'j': n2})
+    assert b.l == 5.0 and b.EA == 30. and b.EI == 20. and math.isclose(b.direction, math.atan2(4, 3))
+    assert b.mass_matrix == 'consistent' and b.nodes == (n1, n2)
+    s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
+    assert sorted(s.solver) == ['buckling', 'linear static', 'modal'] and not s.results['modal'].solved
+    assert s.position_in_matrix(nodeID=2, DOF='rotz') == 5 and s.position_in_matrix(nodeID=2, dynam='FY') == 4
+    assert s.nodenr_dof_from_position(5) == (2, 'MZ')
+    assert s.solver['linear static'].solve() is False            # no loads: Solver.py:79-80
+    with pytest.raises(Exception):
+        s.add_nodal_load(nodeID=7, dynam={'FX': 1})
+    s.add_nodal_load(nodeID=2, dynam={'FX': 1.0})
+    s.add_nodal_load(nodeID=2, dynam={'FX': 2.0, 'MZ': 1.0})
+    assert np.asarray(s.load_vector).ravel().tolist() == [0, 0, 0, 3.0, 0, 1.0]
+    s.add_nodal_load(nodeID=2, dynam={'FY': 5.0}, clear=True)   # clear wipes nodal AND beam loads
+    assert np.asarray(s.load_vector).ravel().tolist() == [0, 0, 0, 0, 5.0, 0]
+    s.add_nodal_mass(nodeID=2, mass={'mx': 2.0})
+    assert np.asarray(s.mass_vector).ravel().tolist() == [0, 0, 0, 2.0, 0, 0]
+    s.set_mass_matrix_type('lumped')
+    assert b.mass_matrix == 'lumped'
+    m = np.matrix(np.arange(36.).reshape(6, 6))
+    assert s.condense(m).shape == (3, 3) and s.condense(m)[0, 0] == 21.
+    # beam loads: local fixed-end vectors and their global rotation (Loads.py:100-112)
+    s.add_internal_loads(beam=b, loadtype='uniform perpendicular force', value=-2.0)
+    r = b.internal_loads[-1].reactions_asvector
+    assert np.allclose(r, [[0, -5.0, -50 / 12., 0, -5.0, 50 / 12.]])
+    glob = b.internal_loads[-1].reactions[n2]
+    assert math.isclose(glob['FX'], 0.8 * 5.0) and math.isclose(glob['FY'], -0.6 * 5.0)
+    assert b.internal_action_points[0] == 0 and b.internal_action_points[-1] == 1
+    with pytest.raises(AssertionError):
+        b.add_internal_load(loadtype='nonsense', value=1)
+    assert set(Loads.BEAM_LOAD_TYPES) == set(rh_beam_load_types())
+
+
+def rh_beam_load_types():
+    from oracle import beamfe2_oracle as orc
+    return orc.BEAM_LOAD_KINDS
+
+
+# ------------------------------------------------------------------------------------ GPU
+gpu = pytest.mark.gpu
+
+
+@gpu
+def test_unit_beam_matrices():
+    """Tests/test_beam_linear_elastic.py:37-70."""
+    n1, n2 = Node.Node(ID=1, coords=(0, 0)), Node.Node(ID=2, coords=(1, 0))
+    b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=1., I=1., A=1., rho=1.)
+    exp = np.array([[1, 0, 0, -1, 0, 0], [0, 12, 6, 0, -12, 6], [0, 6, 4, 0, -6, 2], [-1, 0, 0, 1, 0, 0],
+                    [0, -12, -6, 0, 12, -6], [0, 6, 2, 0, -6, 4]], dtype=float)
+    assert np.allclose(b.Ke, exp, atol=ATOL)
+    assert np.allclose(b.Ke, b.Ke.T, atol=ATOL)
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.cholesky(b.Ke)
+    s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
+    assert s.stiffness_matrix_is_symmetric and s.node_numbering_is_ok and s.stiffness_matrix_is_ok
+    assert np.allclose(s.K, exp, atol=ATOL)
+    assert s.K_with_BC[0, 0] > 1e40
+    free = Structure.Structure(beams=[b], supports={})
+    assert not free.stiffness_matrix_is_nonsingular
+
+
+@gpu
+def test_cantilever_tip_loads_closed_form():
+    """Tests/test_beam_linear_elastic.py:72-115, 162-222 -- one element, also rotated by atan(0.5)."""
+    E, A, I = 2.1e5, 30.0, 22.5
+    for (x, y) in ((100.0, 0.0), (200.0, 100.0)):
+        n1, n2 = Node.Node(ID=1, coords=(0, 0)), Node.Node(ID=2, coords=(x, y))
+        b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=E, I=I, A=A, rho=7.85e-9)
+        s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
+        L, al = b.l, b.direction
+        P = 123.0
+        # axial load along the member, transverse load, end moment
+        s.add_nodal_load(nodeID=2, dynam={'FX': P * math.cos(al), 'FY': P * math.sin(al)}, clear=True)
+        assert s.solver['linear static'].solve() is True
+        d = s.results['linear static'].element_displacements(local=True, beam=b, asvector=True)
+        assert math.isclose(d[3, 0], P * L / (E * A), rel_tol=1e-10) and abs(d[4, 0]) < 1e-9 * abs(d[3, 0]) + 1e-12
+        s.add_nodal_load(nodeID=2, dynam={'FX': -P * math.sin(al), 'FY': P * math.cos(al)}, clear=True)
+        s.solver['linear static'].solve()
+        d = s.results['linear static'].element_displacements(local=True, beam=b, asvector=True)
+        assert math.isclose(d[4, 0], P * L ** 3 / (3 * E * I), rel_tol=1e-10)
+        assert math.isclose(d[5, 0], P * L ** 2 / (2 * E * I), rel_tol=1e-10)
+        s.add_nodal_load(nodeID=2, dynam={'MZ': P}, clear=True)
+        s.solver['linear static'].solve()
+        d = s.results['linear static'].element_displacements(local=True, beam=b, asvector=True)
+        assert math.isclose(d[4, 0], P * L ** 2 / (2 * E * I), rel_tol=1e-10)
+        assert math.isclose(d[5, 0], P * L / (E * I), rel_tol=1e-10)
+        g = s.results['linear static'].global_displacements()
+        assert sorted(g) == ['rotz', 'ux', 'uy'] and g['ux'].shape == (2, 1)
+
+
+@gpu
+@pytest.mark.parametrize('case', ['allresults_1', 'allresults_2', 'allresults_4', 'chopra_105', 'three_elements',
+                                  'clamped_clamped_loads', 'cantilever_example', 'p20_v2'])
+def test_static_through_dropin(case):
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    s = build(model)
+    fixed = np.array(s.positions_to_eliminate, dtype=int)
+    keep = np.setdiff1d(np.arange(s.sumdof), fixed)
+    for c, lc in enumerate(model['load_cases']):
+        apply(s, lc)
+        assert s.solver['linear static'].solve() is True
+        res = s.results['linear static']
+        assert res.solved
+        u = np.asarray(res.displacement_results[0]).ravel()
+        assert res.displacement_results[0].shape == (s.sumdof, 1)
+        if len(keep):
+            assert util.relmax(u[keep], g['u'][c][keep]) < 1e-9
+        r = np.asarray(res.reaction_forces_asvector).ravel()
+        assert util.relmax(r, g['reactions'][c]) < 1e-9
+        for e, b in enumerate(s.beams):
+            d = res.element_displacements(local=True, beam=b, asvector=True)
+            q = np.asarray(b.nodal_reactions_asvector(disps=d)).ravel()
+            assert np.abs(q - g['endforces'][c][e]).max() <= 1e-9 * np.abs(g['endforces'][c]).max()
+            assert np.abs(res.element_end_forces[e] - g['endforces'][c][e]).max() <= 1e-9 * np.abs(g['endforces'][c]).max()
+    rf = s.results['linear static'].reaction_forces
+    assert sorted(rf) == sorted(model['supports'])
+
+
+@gpu
+def test_allresults_asserted_values():
+    """Tests/test_beam_allresults.py:43-113, 311-349 with the reference's own tolerances."""
+    m = util.golden_models()['allresults_1']
+    s = build(m)
+    apply(s, m['load_cases'][0])
+    s.solver['linear static'].solve()
+    exp_r = [0, 481.971154, 0, 0, 0, 0, 0, 608.173077, 0, 0, 0, 0, 0, 4848.557692, 0, 0, 0, 0, 1000., 10061.298077,
+             -1739182.692308]
+    assert np.allclose(np.asarray(s.results['linear static'].reaction_forces_asvector).ravel(), exp_r, atol=1e-5)
+    s.solver['modal'].solve()
+    exp_f = [7.613434040661384, 11.09323127793537, 15.326172330326486, 32.693985190216615, 41.63737293315384,
+             54.555488726848836, 84.23566717176273, 110.95431530916404, 138.32201256527927, 432.24810222320696,
+             1326.485590168174, 2310.0531736149446, 3428.9430318147342, 4633.931252454926, 5560.428871743147]
+    assert np.allclose(s.results['modal'].frequencies, exp_f, atol=1e-5)
+    assert np.allclose(s.results['modal'].periods, [1 / f for f in exp_f], rtol=1e-6)
+    s.add_nodal_mass(nodeID=4, mass={'mx': 1, 'my': 1})
+    s.solver['modal'].solve()
+    assert np.allclose(s.results['modal'].frequencies[0:5], [0.10469612329002663, 9.231045221012806, 10.311990761936627,
+                                                             13.586565471302825, 32.34979734510168], atol=1e-5)
+    m = util.golden_models()['allresults_4']
+    s = build(m)
+    apply(s, m['load_cases'][0])
+    s.solver['linear static'].solve()
+    beam = s.beams[0]
+    disp = s.results['linear static'].element_displacements(local=True, beam=beam, asvector=True)
+    assert abs(beam.internal_action(disp=disp, action='axial', pos=0.) - 1000) < 1e-6
+    assert abs(beam.internal_action(disp=disp, action='axial', pos=0.5) - 750) < 1e-6
+    assert abs(beam.internal_action(disp=disp, action='axial', pos=1.) - 500) < 1e-6
+    assert abs(beam.internal_action(disp=disp, action='moment', pos=0.)) < 1e-3
+    assert abs(beam.internal_action(disp=disp, action='shear', pos=0.5) - 1000) < 1e-6
+    with pytest.raises(AssertionError):
+        beam.internal_action(action='axial', pos=1.2, disp=disp)
+    with pytest.raises(AssertionError):
+        beam.internal_action(action='woos', pos=0.2, disp=disp)
+    assert s.results['linear static'].reaction_forces == {7: {'FX': 500.0, 'FY': 1000.0, 'MZ': -3000000.0}}
+
+
+@gpu
+@pytest.mark.parametrize('case', ['chopra_102', 'chopra_103', 'cantilever_example', 'allresults_2_mass'])
+def test_modal_through_dropin(case):
+    model = util.golden_models()[case]
+    g = util.golden(case)
+    s = build(model)
+    assert s.solver['modal'].solve() is True
+    res = s.results['modal']
+    w = np.array(res.circular_frequencies)
+    assert w.shape == g['circular_freq'].shape
+    assert np.abs(w / g['circular_freq'] - 1).max() < 1e-9
+    assert len(res.displacement_results) == len(g['shapes']) and res.modeshape(0).shape == (s.sumdof, 1)
+    shapes = np.stack([np.asarray(x).ravel() for x in res.displacement_results])
+    assert util.mode_err(shapes[:3], g['shapes'][:3]).max() < 1e-8
+    M = np.asarray(s.M_with_masses)
+    assert util.relmax(M, g['M_with_masses']) < 1e-14
+    assert np.abs(shapes @ M @ shapes.T - np.eye(len(shapes))).max() < 1e-9
+
+
+@gpu
+def test_modal_returns_false_without_mass():
+    n1, n2 = Node.Node(ID=1, coords=(0, 0)), Node.Node(ID=2, coords=(1, 0))
+    b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=1., I=1., A=1., rho=0.)
+    s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
+    assert s.solver['modal'].solve() is False and not s.results['modal'].solved
