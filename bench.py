@@ -266,6 +266,10 @@ def run_gpu_arm(args):
     table = bdist.gather_summaries(bdist.summarize(out['u'], out['lam'], out['info']), B * world)
     n_bad = int((table[:, 0] != 0).sum().item())
 
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return 0
     peaks = {}
