@@ -15,6 +15,9 @@ SYMBOLS = (
     'bfe2_plan_smem_bytes', 'bfe2_workspace_bytes',
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
     'bfe2_solve_fused',
+    'bfe2_plan_create_dense', 'bfe2_sym_eig_dense',
+    'bfe2_beam_create', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve', 'bfe2_beam_matvec',
+    'bfe2_gram_workspace_bytes', 'bfe2_gram64', 'bfe2_update64',
 )
 
 ARR_CONN, ARR_FREE_OF_POS, ARR_POS_OF_FREE, ARR_FIXED, ARR_SLOT_PTR, ARR_CONTRIB, ARR_NODE_PTR, \
@@ -74,13 +77,26 @@ def lib():
     L.bfe2_modal_solve.argtypes = [vp, i64, i32] + [vp] * 7
     L.bfe2_solve_fused.restype = C.c_int
     L.bfe2_solve_fused.argtypes = [vp, i64, i32, i32, i32] + [vp] * 13
-    if hasattr(L, 'bfe2_beam_static'):
-        L.bfe2_beam_workspace_bytes.restype = sz
-        L.bfe2_beam_workspace_bytes.argtypes = [i64, i32]
-        L.bfe2_beam_static.restype = C.c_int
-        L.bfe2_beam_static.argtypes = [i64] + [vp] * 7
-        L.bfe2_beam_modal.restype = C.c_int
-        L.bfe2_beam_modal.argtypes = [i64, i32, i32, i32, C.c_double] + [vp] * 9
+    L.bfe2_plan_create_dense.restype = C.c_int
+    L.bfe2_plan_create_dense.argtypes = [C.POINTER(vp), i32]
+    L.bfe2_sym_eig_dense.restype = C.c_int
+    L.bfe2_sym_eig_dense.argtypes = [vp, i64] + [vp] * 8
+    L.bfe2_beam_create.restype = C.c_int
+    L.bfe2_beam_create.argtypes = [C.POINTER(vp), i64, vp, vp, vp, i32, vp]
+    L.bfe2_beam_destroy.restype = None
+    L.bfe2_beam_destroy.argtypes = [vp]
+    L.bfe2_beam_dims.restype = C.c_int
+    L.bfe2_beam_dims.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.bfe2_beam_solve.restype = C.c_int
+    L.bfe2_beam_solve.argtypes = [vp, i32, vp, vp, vp]
+    L.bfe2_beam_matvec.restype = C.c_int
+    L.bfe2_beam_matvec.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.bfe2_gram_workspace_bytes.restype = sz
+    L.bfe2_gram_workspace_bytes.argtypes = [i64]
+    L.bfe2_gram64.restype = C.c_int
+    L.bfe2_gram64.argtypes = [i64, vp, vp, vp, vp, vp]
+    L.bfe2_update64.restype = C.c_int
+    L.bfe2_update64.argtypes = [i64, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -30,6 +30,20 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+}  // namespace
+
+// shared with bfe2_beam.cu
+int bfe2_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+namespace {
 #define BFE2_CUDA(call)                                                                         \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \
@@ -610,6 +624,50 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         return 0;
     }
     return dispatch_solve<true>(plan, A, (cudaStream_t)stream);
+}
+
+
+// ---- small dense generalized symmetric eigenproblem A q = theta B q (Rayleigh-Ritz step of the subspace
+//      iteration): the same Cholesky-reduction + Jacobi kernel on a synthetic "plan" with identity maps ---
+int bfe2_plan_create_dense(bfe2_plan** out, int32_t n) {
+    if (!out || n < 1 || n > BFE2_MAX_JACOBI_N) return fail(-1, "bfe2_plan_create_dense: n must be in 1..%d", BFE2_MAX_JACOBI_N);
+    bfe2_plan* p = new bfe2_plan();
+    p->nN = 0; p->nE = 0; p->sumdof = n; p->n = n; p->hbw = n - 1; p->nslots = n * n; p->ncontrib = 0;
+    p->free_of_pos.resize(n);
+    p->pos_of_free.resize(n);
+    for (int i = 0; i < n; ++i) p->free_of_pos[i] = p->pos_of_free[i] = i;
+    p->slot_ptr.assign(1, 0);
+    p->node_ptr.assign(1, 0);
+    p->npad = n + (n & 1);
+    jacobi_config(n, &p->rpl, &p->lpp);
+    p->LD = p->rpl * p->lpp;
+    p->nthreads = 64;
+    *out = p;
+    return 0;
+}
+
+namespace {
+__global__ void k_dense_to_band(int n, long long B, const double* __restrict__ A, double* __restrict__ Ab) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n * n) return;
+    const long long b = t / (n * n);
+    const int r = (int)(t % (n * n));
+    const int d = r / n, j = r % n;                     // Ab[d][j] = A[j+d][j]
+    Ab[t] = (j + d < n) ? A[b * n * n + (long long)(j + d) * n + j] : 0.0;
+}
+}  // namespace
+
+int bfe2_sym_eig_dense(bfe2_plan* plan, int64_t B, const double* A, const double* Bm, double* lam, double* V,
+                       int32_t* info, int32_t* sweeps, double* workspace, void* stream) {
+    if (plan && B == 0) return 0;
+    if (!plan || B < 0 || !A || !Bm || !lam || !V || !info || !workspace) return fail(-1, "bfe2_sym_eig_dense: bad argument");
+    if (plan->nE != 0 || plan->hbw != plan->n - 1) return fail(-1, "bfe2_sym_eig_dense needs a plan from bfe2_plan_create_dense");
+    const int n = plan->n;
+    const long long tot = B * n * n;
+    k_dense_to_band<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, B, A, workspace);
+    k_dense_to_band<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, B, Bm, workspace + tot);
+    BFE2_CUDA(cudaGetLastError());
+    return bfe2_modal_solve(plan, B, n, workspace, workspace + tot, lam, V, info, sweeps, stream);
 }
 
 }  // extern "C"

@@ -124,6 +124,35 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
                      double* u, double* endforces, double* reactions,
                      double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream);
 
+/* ---- small dense generalized symmetric eigenproblem A q = theta B q, A, B [Bt, n, n] row-major, B SPD
+ *      (the Rayleigh-Ritz step of the subspace iteration below; same Cholesky-reduction + Jacobi kernel).
+ *      V [Bt, n, n]: row k = k-th eigenvector, V B V^T = I.  workspace: 2*Bt*n*n doubles. ------------- */
+int bfe2_plan_create_dense(bfe2_plan** out, int32_t n);
+int bfe2_sym_eig_dense(bfe2_plan* dense_plan, int64_t Bt, const double* A, const double* Bm, double* lam,
+                       double* V, int32_t* info, int32_t* sweeps, double* workspace, void* stream);
+
+/* ---- one LARGE chain structure (one beam, 1e5 elements).  The reference cannot
+ *      run this size at all (helpers.py:17 allocates a dense sumdof^2 matrix); the CPU comparators are
+ *      scipy.linalg.solveh_banded and scipy.sparse.linalg.eigsh(sigma=0).
+ *      coords [n_elem+1, 2], props [n_elem, 4] are DEVICE pointers, fixed_mask [3 (n_elem+1)] a HOST
+ *      pointer (1 = supported DOF, Structure.py:164-181).  The handle owns the block-tridiagonal K, M and
+ *      the partitioned Cholesky factor of K (device memory, freed by bfe2_beam_destroy).
+ *      Multi-vectors are [n_dof, nrhs] row-major (the nrhs values of a DOF are contiguous). ------------ */
+typedef struct bfe2_beam bfe2_beam;
+int  bfe2_beam_create(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
+                      const uint8_t* fixed_mask, int32_t n_partitions /*0 = auto*/, void* stream);
+void bfe2_beam_destroy(bfe2_beam* beam);
+int  bfe2_beam_dims(const bfe2_beam* beam, int64_t* n_nodes, int64_t* n_dof, int32_t* n_partitions);
+/* U = K^-1 F (Solver.py:76-87 on the condensed system; supported DOFs come out 0 when F is 0 there) */
+int  bfe2_beam_solve(bfe2_beam* beam, int32_t nrhs, const double* F, double* U, void* stream);
+/* Y = K X (which = 0) or Y = M X (which = 1) */
+int  bfe2_beam_matvec(bfe2_beam* beam, int32_t which, int32_t nrhs, const double* X, double* Y, void* stream);
+/* FP64 tensor-core (DMMA) contractions for blocks of exactly 64 vectors:
+ *   C [64,64] = X^T Y  for X, Y [n, 64];   Xout [n,64] = Z [n,64] * Q [64,64] */
+size_t bfe2_gram_workspace_bytes(int64_t n);
+int  bfe2_gram64(int64_t n, const double* X, const double* Y, double* C, double* workspace, void* stream);
+int  bfe2_update64(int64_t n, const double* Z, const double* Q, double* Xout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
