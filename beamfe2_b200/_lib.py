@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbfe2.so')
+LIB_PATH = os.environ.get('BFE2_LIB', os.path.join(_HERE, 'libbfe2.so'))   # BFE2_LIB: A/B builds only
 
 # every symbol include/bfe2.h declares (tests check the library exports exactly these)
 SYMBOLS = (

@@ -270,7 +270,15 @@ k_solve(PlanDev P, BatchArgs A) {
         stage_geometry(P, smem + L.coords, smem + L.geo, tid, nt);
     }
     // band Cholesky: warp 0 -> K, warp 1 -> M (concurrently)
-    if (warp == 0) {
+    if (P.hbw <= 8) {                                // narrow band: one thread per matrix, window in registers
+        if (tid == 0) {
+            s_flag[0] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Kb, smem + L.invK, n, P.hbw)
+                                   : band_cholesky_thread<8>(smem + L.Kb, smem + L.invK, n, P.hbw);
+        } else if (tid == 32 && A.do_modal) {
+            s_flag[1] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Mb, smem + L.invM, n, P.hbw)
+                                   : band_cholesky_thread<8>(smem + L.Mb, smem + L.invM, n, P.hbw);
+        }
+    } else if (warp == 0) {
         const int r = band_cholesky_warp(smem + L.Kb, smem + L.invK, n, P.hbw, lane);
         if (lane == 0) s_flag[0] = r;
     } else if (warp == 1 && A.do_modal) {

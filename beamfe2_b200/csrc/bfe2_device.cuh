@@ -51,11 +51,31 @@ __host__ __device__ inline SmemLayout make_layout(int nN, int nE, int n, int hbw
     L.invM = o;   o += n;
     o = (o + 1) & ~1;                                   // 16-byte align the big region
     L.U = o;
-    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 256) ? 256 : npad * LD);
+    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 384) ? 384 : npad * LD);
     L.lam = o;    o += npad;
     L.order = o;  o += (npad + 1) / 2 + 1;              // npad int32 + 2 flags, stored in double slots
     L.total = o;
     return L;
+}
+
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) and
+// two Newton steps.  Arguments here are finite, normal and positive-or-signed (rcp) -- no special cases.
+__device__ __forceinline__ double rcp_fast(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -243,6 +263,90 @@ __device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, i
     return 0;
 }
 
+// ---- narrow bands (hbw <= HB <= 8): the same factorisation / substitutions by ONE THREAD with the active
+//      window in registers.  The dependent chain per column is rsqrt -> mul -> fma (no shared-memory round
+//      trip, no warp sync), and per substitution row one fma + one mul: these stages are pure latency, and
+//      their latency is time the block does not spend in the Jacobi sweeps.
+template <int HB>
+__device__ __forceinline__ int band_cholesky_thread(double* Ab, double* invdiag, int n, int b) {
+    double w[HB + 1][HB + 1];                        // w[i][j] = current A[col+i][col+j], j <= i
+#pragma unroll
+    for (int i = 0; i <= HB; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+            w[i][j] = (i - j <= b && i < n) ? Ab[(i - j) * n + j] : 0.0;
+    for (int col = 0; col < n; ++col) {
+        const double piv = w[0][0];
+        const double orig = Ab[col];                 // the slot still holds the original diagonal
+        if (!(piv > 1.4210854715202004e-14 * orig) || !isfinite(piv)) return col + 1;
+        const double r = rsqrt_fast(piv);
+        double l[HB + 1];
+#pragma unroll
+        for (int i = 1; i <= HB; ++i) l[i] = w[i][0] * r;
+        Ab[col] = piv * r;
+        invdiag[col] = r;
+#pragma unroll
+        for (int i = 1; i <= HB; ++i)
+            if (i <= b && col + i < n) Ab[i * n + col] = l[i];
+        // trailing update and shift of the window by one row / column
+#pragma unroll
+        for (int i = 1; i <= HB; ++i)
+#pragma unroll
+            for (int j = 1; j <= i; ++j) w[i - 1][j - 1] = fma(-l[i], l[j], w[i][j]);
+        const int row = col + 1 + HB;                // new last row of the window
+#pragma unroll
+        for (int j = 0; j <= HB; ++j) {
+            const int d = HB - j;                    // A[row][col+1+j]
+            w[HB][j] = (d <= b && row < n) ? Ab[d * n + col + 1 + j] : 0.0;
+        }
+    }
+    return 0;
+}
+
+// x <- (L L^T)^-1 x (FWD && BWD) or x <- L^-T x (BWD only); xin/xout may alias; stride = distance of rows
+template <int HB, bool FWD, bool BWD>
+__device__ __forceinline__ void band_subst_thread(const double* Lb, const double* invdiag, double* x, int stride,
+                                                  int n, int b, int first = 0) {
+    if (FWD) {
+        double win[HB];                              // win[d-1] = x[j-d]
+#pragma unroll
+        for (int d = 0; d < HB; ++d) win[d] = 0.0;
+        for (int j = first; j < n; ++j) {
+            double far = x[j * stride];
+#pragma unroll
+            for (int d = 2; d <= HB; ++d) {
+                const double lc = (d <= b && j - d >= first) ? Lb[d * n + (j - d)] : 0.0;
+                far = fma(-lc, win[d - 1], far);
+            }
+            const double l1 = (1 <= b && j - 1 >= first) ? Lb[n + (j - 1)] : 0.0;
+            const double v = fma(-l1, win[0], far) * invdiag[j];
+#pragma unroll
+            for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
+            win[0] = v;
+            x[j * stride] = v;
+        }
+    }
+    if (BWD) {
+        double win[HB];                              // win[d-1] = x[j+d]
+#pragma unroll
+        for (int d = 0; d < HB; ++d) win[d] = 0.0;
+        for (int j = n - 1; j >= first; --j) {
+            double far = x[j * stride];
+#pragma unroll
+            for (int d = 2; d <= HB; ++d) {
+                const double lc = (d <= b && j + d < n) ? Lb[d * n + j] : 0.0;
+                far = fma(-lc, win[d - 1], far);
+            }
+            const double l1 = (1 <= b && j + 1 < n) ? Lb[n + j] : 0.0;
+            const double v = fma(-l1, win[0], far) * invdiag[j];
+#pragma unroll
+            for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
+            win[0] = v;
+            x[j * stride] = v;
+        }
+    }
+}
+
 // Forward + back substitution with the band factor, one thread per right-hand side (in place).
 __device__ __forceinline__ void band_solve_thread(const double* Lb, const double* invdiag, double* x, int n, int b) {
     for (int j = 0; j < n; ++j) {                    // L y = f
@@ -301,7 +405,11 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
     }
     __syncthreads();
     // 2. one thread per load case: L L^T u = f
-    for (int c = tid; c < C; c += nt) band_solve_thread(s_Kb, s_invK, s_f + c * n, n, P.hbw);
+    for (int c = tid; c < C; c += nt) {
+        if (P.hbw <= 5) band_subst_thread<5, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
+        else if (P.hbw <= 8) band_subst_thread<8, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
+        else band_solve_thread(s_Kb, s_invK, s_f + c * n, n, P.hbw);
+    }
     __syncthreads();
     // 3. expand to all DOFs (exact zeros at supports), write u
     for (int t = tid; t < C * sumdof; t += nt) {
@@ -463,41 +571,34 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
 //   row-halves of the dot product meet through 2 x 8 bytes of shared memory per lane and one
 //   __syncthreads per step; both warps then compute bit-identical rotation parameters.
 // ------------------------------------------------------------------------------------------------
-// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits) and
-// two Newton steps.  Arguments here are finite, normal and positive-or-signed (rcp) -- no special cases.
-__device__ __forceinline__ double rcp_fast(double a) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-    double e = fma(-a, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-a, x, 1.0);
-    return fma(x, e, x);
+// shared-memory access through 32-bit shared-window addresses (saves the generic->shared conversion that
+// the compiler otherwise re-materialises around every barrier)
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-__device__ __forceinline__ double rsqrt_fast(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double h = 0.5 * a;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    return fma(y, e, y);
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
+
+// One step of the odd-even ordering, software-pipelined: the rotation of the resident pair, the cyclic
+// shuffle of the moving column and the dot product of the NEXT pairing are fused in one straight-line loop
+// over the rows, so that a single warp keeps the FP64 pipe (rotation + dot FMAs) and the shuffle path busy
+// at the same time.  On entry g is the dot product of the resident pair; on exit the partial dot product of
+// the next pairing has been stored to shared memory (pg_mine).
+#ifndef BFE2_ABLATE
+#define BFE2_ABLATE 0      // timing experiments only: 1 no shuffles, 2 no rotation FMAs, 4 no exchange, 8 no rot math
+#endif
+#if BFE2_ABLATE & 1
+#define BFE2_SHFL(v, src) (v)
+#else
+#define BFE2_SHFL(v, src) __shfl_sync(0xffffffffu, v, src)
+#endif
 
 template <int RPL, bool ODD>
 __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
-                                                 int& rotated, double* pg, int h, int lane, bool act, bool last,
-                                                 int src) {
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-#pragma unroll
-    for (int r = 0; r + 3 < RPL; r += 4) {
-        g0 = fma(A[r], B[r], g0); g1 = fma(A[r + 1], B[r + 1], g1);
-        g2 = fma(A[r + 2], B[r + 2], g2); g3 = fma(A[r + 3], B[r + 3], g3);
-    }
-#pragma unroll
-    for (int r = RPL & ~3; r < RPL; ++r) g0 = fma(A[r], B[r], g0);
-    pg[h * 32 + lane] = (g0 + g1) + (g2 + g3);
-    __syncthreads();
-    const double g = pg[lane] + pg[32 + lane];
+                                                 int& rotated, double g, unsigned pg_mine, bool act, bool last, int src) {
     // rotate when |g| > tol * sqrt(nA nB)  <=>  g^2 > tol^2 nA nB
     const bool rot = act && !(ODD && last) && (g * g > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * (nA * nB));
     double c = 1.0, s = 0.0;
@@ -505,35 +606,55 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
         c = 0.0; s = -1.0;                            // immaterial: columns are defined up to sign)
         const double tmp = nA; nA = nB; nB = tmp;
     }
+#if BFE2_ABLATE & 8
+    if (rot) { c = 0.8; s = 0.6; rotated = 1; }
+    if (false) {
+#else
     if (rot) {
-        // tan(2 theta) = 2g / (nB - nA);  t = tan(theta) is the smaller root:  t = h / (d + sign(d) sqrt(d^2+h^2))
+#endif
+        // tan(2 theta) = h / d, h = 2g, d = nB - nA, |theta| <= pi/4:
+        //   cos(2 theta) = |d| / r, sin(2 theta) = sign(d) h / r, r = sqrt(d^2 + h^2)
+        //   c^2 = (1 + cos 2theta) / 2,  s = sin(2 theta) / (2 c),  t = s / c
         const double d = nB - nA, hh = 2.0 * g;
-        const double q = fma(d, d, hh * hh);
-        const double rq = q * rsqrt_fast(q);                       // sqrt(d^2 + h^2)
-        const double t = hh * rcp_fast(d + copysign(rq, d));
-        c = rsqrt_fast(fma(t, t, 1.0));
-        s = c * t;
-        nA = fma(-t, g, nA);
-        nB = fma(t, g, nB);
+        const double ir = rsqrt_fast(fma(d, d, hh * hh));
+        const double hs = (d < 0.0) ? -hh : hh;       // sign(d) h
+        const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+        const double ic = rsqrt_fast(c2);             // 1 / c
+        c = c2 * ic;
+        s = (0.5 * hs * ir) * ic;
+        const double tg = (s * ic) * g;               // t g
+        nA -= tg;
+        nB += tg;
         rotated = 1;
     }
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+#if BFE2_ABLATE & 2
+    if (false) {
+#else
     if (__any_sync(0xffffffffu, rot || (ODD && last && act))) {
+#endif
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const double sb = s * B[r], cb = c * B[r];
-            B[r] = fma(s, A[r], cb);
-            A[r] = fma(c, A[r], -sb);
+            const double nb = fma(s, A[r], cb);
+            const double na = fma(c, A[r], -sb);
+            if (!ODD) { A[r] = na; B[r] = BFE2_SHFL(nb, src); }
+            else { B[r] = nb; A[r] = BFE2_SHFL(na, src); }
+            acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
+        }
+    } else {                                          // nobody in this warp rotates: move and multiply only
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            if (!ODD) B[r] = BFE2_SHFL(B[r], src);
+            else A[r] = BFE2_SHFL(A[r], src);
+            acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
         }
     }
-    if (!ODD) {
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) B[r] = __shfl_sync(0xffffffffu, B[r], src);
-        nB = __shfl_sync(0xffffffffu, nB, src);
-    } else {
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) A[r] = __shfl_sync(0xffffffffu, A[r], src);
-        nA = __shfl_sync(0xffffffffu, nA, src);
-    }
+    if (!ODD) nB = __shfl_sync(0xffffffffu, nB, src);
+    else nA = __shfl_sync(0xffffffffu, nA, src);
+    sts_f64(pg_mine, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
 }
 
 template <int RPL>
@@ -555,33 +676,54 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
         }
     }
     __syncthreads();                                  // W is in registers: its memory becomes scratch
-    double* part_g = s_W;                             // [2 parity][2 warps][32 lanes]
-    double* part_n = s_W + 128;                       // [2 warps][32 lanes][2]
+    const unsigned pg0 = (unsigned)__cvta_generic_to_shared(s_W);      // [2 parity][2 warps][32 lanes]
+    const unsigned pg1 = pg0 + 64u * 8u;
+    const unsigned mine = 8u * (h * 32 + lane), w0 = 8u * lane, w1 = 8u * (32 + lane);
+    double* part_n = s_W + 128;                       // [2 warps][32 lanes][3]
     int sweeps = 0;
     bool converged = false;
     for (; sweeps < max_sweeps; ++sweeps) {
-        // refresh the cached squared norms from the data
-        double nA, nB;
+        // refresh the cached squared norms from the data and form the first dot product of the sweep
+        double nA, nB, g;
         {
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0;
 #pragma unroll
             for (int r = 0; r + 1 < RPL; r += 2) {
                 a0 = fma(A[r], A[r], a0); a1 = fma(A[r + 1], A[r + 1], a1);
                 b0 = fma(B[r], B[r], b0); b1 = fma(B[r + 1], B[r + 1], b1);
+                c0 = fma(A[r], B[r], c0); c1 = fma(A[r + 1], B[r + 1], c1);
             }
-            if (RPL & 1) { a0 = fma(A[RPL - 1], A[RPL - 1], a0); b0 = fma(B[RPL - 1], B[RPL - 1], b0); }
-            part_n[(h * 32 + lane) * 2] = a0 + a1;
-            part_n[(h * 32 + lane) * 2 + 1] = b0 + b1;
+            if (RPL & 1) {
+                a0 = fma(A[RPL - 1], A[RPL - 1], a0); b0 = fma(B[RPL - 1], B[RPL - 1], b0);
+                c0 = fma(A[RPL - 1], B[RPL - 1], c0);
+            }
+            part_n[(h * 32 + lane) * 3] = a0 + a1;
+            part_n[(h * 32 + lane) * 3 + 1] = b0 + b1;
+            part_n[(h * 32 + lane) * 3 + 2] = c0 + c1;
             __syncthreads();
-            nA = part_n[lane * 2] + part_n[(32 + lane) * 2];
-            nB = part_n[lane * 2 + 1] + part_n[(32 + lane) * 2 + 1];
+            nA = part_n[lane * 3] + part_n[(32 + lane) * 3];
+            nB = part_n[lane * 3 + 1] + part_n[(32 + lane) * 3 + 1];
+            g = part_n[lane * 3 + 2] + part_n[(32 + lane) * 3 + 2];
         }
         int rotated = 0;
         for (int step = 0; step < npad; step += 2) {
-            jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, part_g, h, lane, act, last, src_dn);
-            jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, part_g + 64, h, lane, act, last, src_up);
+            jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, g, pg1 + mine, act, last, src_dn);
+#if !(BFE2_ABLATE & 4)
+            __syncthreads();
+            g = lds_f64(pg1 + w0) + lds_f64(pg1 + w1);                 // same order in both warps: identical bits
+#endif
+            jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, g, pg0 + mine, act, last, src_up);
+#if !(BFE2_ABLATE & 4)
+            __syncthreads();
+            g = lds_f64(pg0 + w0) + lds_f64(pg0 + w1);
+#endif
         }
+#if BFE2_ABLATE
+        __syncthreads();
+        if (sweeps == 9) { ++sweeps; converged = true; break; }        // fixed 10 sweeps for timing experiments
+#else
         if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
+#endif
     }
     __syncthreads();                                  // scratch no longer read: W comes back
     if (act) {
@@ -602,11 +744,18 @@ __device__ __forceinline__ void stage_form_gt(const PlanDev& P, const double* s_
     for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
     __syncthreads();
     for (int j = tid; j < n; j += nt) {
-        for (int r = j; r < n; ++r) {
-            double acc = (r - j <= b) ? s_Kb[(r - j) * n + j] : 0.0;
-            const int k0 = max(j, r - b);
-            for (int k = k0; k < r; ++k) acc -= s_Mb[(r - k) * n + k] * s_W[(k + off) * LD + j];
-            s_W[(r + off) * LD + j] = acc * s_invM[r];
+        // right-hand side: column j of Lk, written into the (transposed) slot layout, then L_m^-1 in place
+        double* col = s_W + off * LD + j;            // element r of the column lives at col[r * LD]
+        for (int r = j; r < n && r - j <= b; ++r) col[r * LD] = s_Kb[(r - j) * n + j];
+        if (b <= 5) band_subst_thread<5, true, false>(s_Mb, s_invM, col, LD, n, b, j);
+        else if (b <= 8) band_subst_thread<8, true, false>(s_Mb, s_invM, col, LD, n, b, j);
+        else {
+            for (int r = j; r < n; ++r) {
+                double acc = col[r * LD];
+                const int k0 = max(j, r - b);
+                for (int k = k0; k < r; ++k) acc -= s_Mb[(r - k) * n + k] * col[k * LD];
+                col[r * LD] = acc * s_invM[r];
+            }
         }
     }
     __syncthreads();
@@ -641,7 +790,9 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
     // phi = Lk^-T w, in place in the slot; then fix the sign (largest-magnitude entry positive)
     for (int m = tid; m < n_modes; m += nt) {
         double* w = s_W + s_order[m] * LD;
-        band_backsolve_thread(s_Kb, s_invK, w, n, P.hbw);
+        if (P.hbw <= 5) band_subst_thread<5, false, true>(s_Kb, s_invK, w, 1, n, P.hbw);
+        else if (P.hbw <= 8) band_subst_thread<8, false, true>(s_Kb, s_invK, w, 1, n, P.hbw);
+        else band_backsolve_thread(s_Kb, s_invK, w, n, P.hbw);
         double best = 0.0, sign = 1.0;
         for (int r = 0; r < n; ++r) {
             const double v = fabs(w[r]);
