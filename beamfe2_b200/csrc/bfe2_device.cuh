@@ -587,15 +587,6 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 // over the rows, so that a single warp keeps the FP64 pipe (rotation + dot FMAs) and the shuffle path busy
 // at the same time.  On entry g is the dot product of the resident pair; on exit the partial dot product of
 // the next pairing has been stored to shared memory (pg_mine).
-#ifndef BFE2_ABLATE
-#define BFE2_ABLATE 0      // timing experiments only: 1 no shuffles, 2 no rotation FMAs, 4 no exchange, 8 no rot math
-#endif
-#if BFE2_ABLATE & 1
-#define BFE2_SHFL(v, src) (v)
-#else
-#define BFE2_SHFL(v, src) __shfl_sync(0xffffffffu, v, src)
-#endif
-
 template <int RPL, bool ODD>
 __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
                                                  int& rotated, double g, unsigned pg_mine, bool act, bool last, int src) {
@@ -606,12 +597,7 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
         c = 0.0; s = -1.0;                            // immaterial: columns are defined up to sign)
         const double tmp = nA; nA = nB; nB = tmp;
     }
-#if BFE2_ABLATE & 8
-    if (rot) { c = 0.8; s = 0.6; rotated = 1; }
-    if (false) {
-#else
     if (rot) {
-#endif
         // tan(2 theta) = h / d, h = 2g, d = nB - nA, |theta| <= pi/4:
         //   cos(2 theta) = |d| / r, sin(2 theta) = sign(d) h / r, r = sqrt(d^2 + h^2)
         //   c^2 = (1 + cos 2theta) / 2,  s = sin(2 theta) / (2 c),  t = s / c
@@ -630,25 +616,21 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
     double acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-#if BFE2_ABLATE & 2
-    if (false) {
-#else
     if (__any_sync(0xffffffffu, rot || (ODD && last && act))) {
-#endif
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const double sb = s * B[r], cb = c * B[r];
             const double nb = fma(s, A[r], cb);
             const double na = fma(c, A[r], -sb);
-            if (!ODD) { A[r] = na; B[r] = BFE2_SHFL(nb, src); }
-            else { B[r] = nb; A[r] = BFE2_SHFL(na, src); }
+            if (!ODD) { A[r] = na; B[r] = __shfl_sync(0xffffffffu, nb, src); }
+            else { B[r] = nb; A[r] = __shfl_sync(0xffffffffu, na, src); }
             acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
         }
     } else {                                          // nobody in this warp rotates: move and multiply only
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
-            if (!ODD) B[r] = BFE2_SHFL(B[r], src);
-            else A[r] = BFE2_SHFL(A[r], src);
+            if (!ODD) B[r] = __shfl_sync(0xffffffffu, B[r], src);
+            else A[r] = __shfl_sync(0xffffffffu, A[r], src);
             acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
         }
     }
@@ -708,22 +690,13 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
         int rotated = 0;
         for (int step = 0; step < npad; step += 2) {
             jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, g, pg1 + mine, act, last, src_dn);
-#if !(BFE2_ABLATE & 4)
             __syncthreads();
             g = lds_f64(pg1 + w0) + lds_f64(pg1 + w1);                 // same order in both warps: identical bits
-#endif
             jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, g, pg0 + mine, act, last, src_up);
-#if !(BFE2_ABLATE & 4)
             __syncthreads();
             g = lds_f64(pg0 + w0) + lds_f64(pg0 + w1);
-#endif
         }
-#if BFE2_ABLATE
-        __syncthreads();
-        if (sweeps == 9) { ++sweeps; converged = true; break; }        // fixed 10 sweeps for timing experiments
-#else
         if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
-#endif
     }
     __syncthreads();                                  // scratch no longer read: W comes back
     if (act) {
