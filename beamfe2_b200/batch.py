@@ -137,6 +137,36 @@ def solve_fused(plan: Plan, coords, props, nodal_mass=None, f_nodal=None, r_loca
     return dict(u=u, endforces=ef, reactions=re, lam=lam, phi=phi, info=info, sweeps=sweeps)
 
 
+def internal_actions(plan: Plan, coords, endforces, q_axial=None, q_perp=None, npts=11, want_field=True):
+    """N, V, M along every beam: actions [B,C,nE,3,npts] (or None) and maxabs [B,C,nE,3]."""
+    B, C = endforces.shape[0], endforces.shape[1]
+    dev = endforces.device
+    coords = _chk(coords, (B, plan.n_nodes, 2), 'coords')
+    endforces = _chk(endforces, (B, C, plan.n_elem, 6), 'endforces')
+    q_axial = _chk(q_axial, (B, C, plan.n_elem), 'q_axial')
+    q_perp = _chk(q_perp, (B, C, plan.n_elem), 'q_perp')
+    act = torch.empty((B, C, plan.n_elem, 3, npts), dtype=torch.float64, device=dev) if want_field else None
+    mx = torch.empty((B, C, plan.n_elem, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bfe2_internal_actions(plan.handle, B, C, int(npts), _lib.ptr(coords), _lib.ptr(endforces),
+                                                    _lib.ptr(q_axial), _lib.ptr(q_perp), _lib.ptr(act), _lib.ptr(mx),
+                                                    _stream_ptr()))
+    return act, mx
+
+
+def modal_participation(plan: Plan, Mb, phi):
+    """gamma [B, n_modes, 2] = phi^T M r_x, phi^T M r_y; effective modal masses are gamma ** 2.
+    `plan` / `Mb`: the UNSUPPORTED plan (Plan(n_nodes, conn, [])) and its assembled band mass matrix."""
+    B, n_modes = phi.shape[0], phi.shape[1]
+    Mb = _chk(Mb, (B, plan.hbw + 1, plan.n_free), 'Mb')
+    phi = _chk(phi, (B, n_modes, plan.sumdof), 'phi')
+    gamma = torch.empty((B, n_modes, 2), dtype=torch.float64, device=phi.device)
+    with torch.cuda.device(phi.device):
+        _lib.check(_lib.lib().bfe2_modal_participation(plan.handle, B, n_modes, _lib.ptr(Mb), _lib.ptr(phi),
+                                                       _lib.ptr(gamma), _stream_ptr()))
+    return gamma
+
+
 class HostPipeline:
     """End-to-end path with HOST buffers: pinned host tensors -> H2D -> fused kernel -> D2H, chunked
     over a few CUDA streams so that copies overlap the kernels.  This is the call a user of the

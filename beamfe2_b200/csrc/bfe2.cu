@@ -115,6 +115,12 @@ int plan_upload(bfe2_plan* p) {
 
 }  // namespace
 
+// shared with bfe2_post.cu: device view of a plan (uploads lazily); NULL + last_error on failure
+const PlanDev* bfe2_plan_device_view(bfe2_plan* plan) {
+    if (plan_upload(plan) != 0) return nullptr;
+    return &plan->dev;
+}
+
 // =================================================================================================
 // kernels
 // =================================================================================================

@@ -166,33 +166,34 @@ __device__ __forceinline__ void beam_geometry(double xi, double yi, double xj, d
 // Block-level stages.  `tid`/`nt` = thread index / count inside the block.
 // ------------------------------------------------------------------------------------------------
 
-// Stage E: geometry + global 6x6 K and M of every beam into shared memory.
+// Stage E: geometry + global 6x6 K and M of every beam into shared memory.  Work item = (beam, matrix):
+// with 2 nE <= blockDim the stiffness and mass matrices of all beams are formed concurrently.
 __device__ __forceinline__ void stage_elements(const PlanDev& P, const double* s_coords, const double* s_props,
                                                double* s_geo, double* s_Ke, double* s_Me, bool want_mass,
                                                int tid, int nt) {
-    for (int e = tid; e < P.nE; e += nt) {
+    const int items = want_mass ? 2 * P.nE : P.nE;
+    for (int it = tid; it < items; it += nt) {
+        const int e = it < P.nE ? it : it - P.nE;
+        const bool mass = it >= P.nE;
         const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
         double L, c, s;
         beam_geometry(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], L, c, s);
-        s_geo[3 * e] = L;
-        s_geo[3 * e + 1] = c;
-        s_geo[3 * e + 2] = s;
         const double E = s_props[4 * e], A = s_props[4 * e + 1], I = s_props[4 * e + 2], rho = s_props[4 * e + 3];
         double X[6][6];
-        ke_local(X, E, A, I, L);
+        if (!mass) {
+            s_geo[3 * e] = L;
+            s_geo[3 * e + 1] = c;
+            s_geo[3 * e + 2] = s;
+            ke_local(X, E, A, I, L);
+        } else {
+            me_local(X, rho, A, L, P.lumped[e] != 0);
+        }
         rotate_to_global(X, c, s);
+        double* dst = (mass ? s_Me : s_Ke) + 36 * e;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) s_Ke[36 * e + 6 * r + q] = X[r][q];
-        if (want_mass) {
-            me_local(X, rho, A, L, P.lumped[e] != 0);
-            rotate_to_global(X, c, s);
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int q = 0; q < 6; ++q) s_Me[36 * e + 6 * r + q] = X[r][q];
-        }
+            for (int q = 0; q < 6; ++q) dst[6 * r + q] = X[r][q];
     }
 }
 

@@ -1,0 +1,112 @@
+// bfe2_post.cu -- post-processing kernels next to the hot path.
+//
+//   bfe2_internal_actions : N / V / M along every beam from the local end forces (HermitianBeam_2D.py:398-431:
+//       axial, shear: -v1; moment: v1 + (-v2 - v1) pos) plus the add-on curves of UNIFORM beam loads
+//       (Loads.py:214-225 axial: -xi q L;  :277-289 shear: -xi L q, moment: xi (1-xi) q L^2 / 2), and the
+//       per-beam maxima the reference lists as future work (todo.md:23).
+//   bfe2_modal_participation : Gamma_k = phi_k^T M r for the rigid-body influence vectors r_x, r_y
+//       (prototype arithmetic in Examples/modal_masses.py:40-49; phi is M-normalised, so the effective modal
+//       mass is Gamma^2).
+#include <cuda_runtime.h>
+
+#include "../../include/bfe2.h"
+#include "bfe2_device.cuh"
+
+using namespace bfe2;
+
+int bfe2_fail(int code, const char* fmt, ...);
+const PlanDev* bfe2_plan_device_view(bfe2_plan* plan);   // bfe2.cu: uploads if needed, NULL on error
+
+namespace {
+
+__global__ void k_internal_actions(PlanDev P, long long B, int C, int npts, const double* __restrict__ coords,
+                                   const double* __restrict__ endforces, const double* __restrict__ q_axial,
+                                   const double* __restrict__ q_perp, double* __restrict__ actions,
+                                   double* __restrict__ maxabs) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = B * C * P.nE;
+    if (t >= total) return;
+    const int e = (int)(t % P.nE);
+    const long long b = t / ((long long)C * P.nE);
+    const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
+    const double* xy = coords + b * 2 * P.nN;
+    double L, c, s;
+    beam_geometry(xy[2 * ni], xy[2 * ni + 1], xy[2 * nj], xy[2 * nj + 1], L, c, s);
+    const double* q = endforces + t * 6;
+    const double qa = q_axial ? q_axial[t] : 0.0, qp = q_perp ? q_perp[t] : 0.0;
+    const double n1 = q[0], v1 = q[1], m1 = q[2], m2 = -q[5];
+    double mx[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < npts; ++k) {
+        const double xi = npts > 1 ? (double)k / (double)(npts - 1) : 0.0;
+        const double ax = -n1 + (-xi * qa * L);
+        const double sh = -v1 + (xi * L * -qp);
+        const double mo = (m1 + (m2 - m1) * xi) + ((xi * (1.0 - xi)) * qp * (L * L)) / 2.0;
+        if (actions) {
+            double* o = actions + t * 3 * npts;
+            o[k] = ax; o[npts + k] = sh; o[2 * npts + k] = mo;
+        }
+        mx[0] = fmax(mx[0], fabs(ax)); mx[1] = fmax(mx[1], fabs(sh)); mx[2] = fmax(mx[2], fabs(mo));
+    }
+    if (maxabs) { maxabs[t * 3] = mx[0]; maxabs[t * 3 + 1] = mx[1]; maxabs[t * 3 + 2] = mx[2]; }
+}
+
+// thread per (structure, mode): Gamma = sum_i phi_i (M r)_i with the lower-band M of the condensed system
+__global__ void k_participation(PlanDev P, long long B, int n_modes, const double* __restrict__ Mb,
+                                const double* __restrict__ phi, double* __restrict__ gamma) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n_modes) return;
+    const long long b = t / n_modes;
+    const int n = P.n, hb = P.hbw;
+    const double* M = Mb + b * P.nslots;
+    const double* f = phi + t * P.sumdof;
+    double gx = 0.0, gy = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double fj = f[P.pos_of_free[j]];
+        const int dj = P.pos_of_free[j] % 3;
+        // column j of M (lower band) couples rows j .. j+hb; use symmetry for the upper part
+        for (int d = 0; d <= hb && j + d < n; ++d) {
+            const double m = M[d * n + j];
+            const int i = j + d;
+            const double fi = f[P.pos_of_free[i]];
+            const int di = P.pos_of_free[i] % 3;
+            // contribution phi_i M_ij r_j  and (d > 0) phi_j M_ji r_i
+            if (dj == 0) gx += fi * m; else if (dj == 1) gy += fi * m;
+            if (d > 0) { if (di == 0) gx += fj * m; else if (di == 1) gy += fj * m; }
+        }
+    }
+    gamma[t * 2] = gx;
+    gamma[t * 2 + 1] = gy;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
+                          const double* endforces, const double* q_axial, const double* q_perp, double* actions,
+                          double* maxabs, void* stream) {
+    if (plan && B == 0) return 0;
+    if (!plan || B < 0 || C < 1 || npts < 1 || !coords || !endforces || (!actions && !maxabs))
+        return bfe2_fail(-1, "bfe2_internal_actions: bad argument");
+    const PlanDev* P = bfe2_plan_device_view(plan);
+    if (!P) return -100;
+    const long long total = B * C * P->nE;
+    k_internal_actions<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, B, C, npts, coords, endforces,
+                                                                                           q_axial, q_perp, actions, maxabs);
+    if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_internal_actions launch failed");
+    return 0;
+}
+
+int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,
+                             double* gamma, void* stream) {
+    if (plan && B == 0) return 0;
+    if (!plan || B < 0 || n_modes < 1 || !Mb || !phi || !gamma) return bfe2_fail(-1, "bfe2_modal_participation: bad argument");
+    const PlanDev* P = bfe2_plan_device_view(plan);
+    if (!P) return -100;
+    const long long total = B * n_modes;
+    k_participation<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, B, n_modes, Mb, phi, gamma);
+    if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_participation launch failed");
+    return 0;
+}
+
+}  // extern "C"

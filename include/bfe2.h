@@ -153,6 +153,21 @@ size_t bfe2_gram_workspace_bytes(int64_t n);
 int  bfe2_gram64(int64_t n, const double* X, const double* Y, double* C, double* workspace, void* stream);
 int  bfe2_update64(int64_t n, const double* Z, const double* Q, double* Xout, void* stream);
 
+/* ---- post-processing next to the hot path.
+ *   internal actions: N, V, M at npts equidistant positions of every beam from the local end forces
+ *     (HermitianBeam_2D.py:398-431) plus the add-on curves of uniform beam loads q_axial / q_perp
+ *     [B, C, nE] or NULL (Loads.py:214-225, 277-289); actions [B, C, nE, 3, npts] and/or
+ *     maxabs [B, C, nE, 3] (either may be NULL).
+ *   modal participation: gamma [B, n_modes, 2] = phi_k^T M r_x, phi_k^T M r_y (Examples/modal_masses.py:40-49;
+ *     effective modal mass = gamma^2).  `plan` and Mb are those of the UNSUPPORTED structure (plan created
+ *     with n_fixed = 0, Mb from bfe2_assemble_banded on it): the reference's arithmetic uses the full M, whose
+ *     columns at the supports couple the ground motion into the free DOFs. */
+int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
+                          const double* endforces, const double* q_axial, const double* q_perp,
+                          double* actions, double* maxabs, void* stream);
+int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,
+                             double* gamma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

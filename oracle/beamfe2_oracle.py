@@ -366,6 +366,34 @@ def internal_action_baseline(endf_e, action, pos):
     return -v1
 
 
+def internal_action_field(endf, L, q_axial=None, q_perp=None, npts=11):
+    """HermitianBeam_2D.py:398-431 + Loads.py:214-225, 277-289 -- N, V, M at npts equidistant positions for
+    uniform beam loads.  endf [..., 6], L [...], q_* [...] -> [..., 3, npts]."""
+    xi = np.linspace(0.0, 1.0, npts) if npts > 1 else np.zeros(1)
+    L = np.asarray(L)[..., None]
+    qa = 0.0 if q_axial is None else np.asarray(q_axial)[..., None]
+    qp = 0.0 if q_perp is None else np.asarray(q_perp)[..., None]
+    n1, v1, m1, m2 = (endf[..., k][..., None] for k in (0, 1, 2, 5))
+    ax = -n1 + (-xi * qa * L)
+    sh = -v1 + (xi * L * -qp)
+    mo = (m1 + (-m2 - m1) * xi) + ((xi * (1 - xi)) * qp * L ** 2) / 2.
+    return np.stack([ax + 0 * xi, sh + 0 * xi, mo], axis=-2)
+
+
+def participation_factors(phi, M):
+    """Examples/modal_masses.py:40-49 -- Gamma = phi^T M r / (phi^T M phi) for r = 1 on the ux (resp. uy) DOFs.
+    phi [..., m, sumdof], M [..., sumdof, sumdof] -> [..., m, 2]."""
+    n = M.shape[-1]
+    out = []
+    for k in (0, 1):
+        r = np.zeros(n)
+        r[k::3] = 1.0
+        num = np.einsum('...mi,...ij,j->...m', phi, M, r)
+        den = np.einsum('...mi,...ij,...mj->...m', phi, M, phi)
+        out.append(num / den)
+    return np.stack(out, axis=-1)
+
+
 # --------------------------------------------------------------------------- whole path
 def solve_batch(conn, fixed, coords, props, nodal_mass=None, f_nodal=None, r_local=None,
                 lumped=None, n_modes=None, static='condensed'):

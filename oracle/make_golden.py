@@ -179,6 +179,47 @@ def mp_truth(n_variants=8, n_modes=10):
     return dict(params=P, lam=lam_t, phi=phi_t, u=u_t)
 
 
+POST_CASES = ('p20_v0', 'p20_v1', 'allresults_1', 'allresults_2', 'chopra_105')
+
+
+def post_golden(models):
+    """Internal-action queries (HermitianBeam2D.internal_action) at 5 positions of every beam and the
+    participation factors of Examples/modal_masses.py:40-49, computed by the REAL reference."""
+    import warnings
+    out = {}
+    pos = [0.0, 0.25, 0.5, 0.75, 1.0]
+    for name in POST_CASES:
+        model = models[name]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            s = rh.build_structure(model)
+            acts = []
+            for lc in model['load_cases']:
+                rh.apply_load_case(s, lc)
+                s.solver['linear static'].solve()
+                res = s.results['linear static']
+                per_beam = []
+                for b in s.beams:
+                    d = res.element_displacements(local=True, beam=b, asvector=True)
+                    per_beam.append([[float(b.internal_action(action=a, disp=d, pos=p)) for p in pos]
+                                     for a in ('axial', 'shear', 'moment')])
+                acts.append(per_beam)
+            out[name + '/internal_actions'] = np.array(acts)
+            s.solver['modal'].solve()
+            m = np.asarray(s.M_with_masses)
+            gam = []
+            for k in range(min(6, len(s.results['modal'].displacement_results))):
+                fi = np.asarray(s.results['modal'].modeshape(k))
+                row = []
+                for comp in (0, 1):
+                    unit = np.zeros((len(m), 1))
+                    unit[comp::3] = 1.0
+                    row.append(float((fi.T @ m @ unit) / (fi.T @ m @ fi)))
+                gam.append(row)
+            out[name + '/gamma'] = np.array(gam)
+    return out
+
+
 def main():
     gold = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(gold, exist_ok=True)
@@ -199,7 +240,9 @@ def main():
     with open(os.path.join(gold, 'ref_cases.json'), 'w') as f:
         json.dump(models, f, default=enc, indent=0)
     np.savez_compressed(os.path.join(gold, 'ref_cases.npz'), **arrays)
-    np.savez_compressed(os.path.join(gold, 'p20_truth.npz'), **mp_truth())
+    np.savez_compressed(os.path.join(gold, 'ref_post.npz'), **post_golden(models))
+    if '--no-truth' not in sys.argv:
+        np.savez_compressed(os.path.join(gold, 'p20_truth.npz'), **mp_truth())
     print('wrote', gold)
 
 
