@@ -70,6 +70,10 @@ namespace {
 
 // Jacobi lane configuration for n free DOFs: RPL rows per lane, LPP lanes per column pair.
 bool jacobi_config(int n, int* rpl, int* lpp) {
+    // BFE2_NW = 3 | 4: experimental row split over 3 / 4 warps per structure (register-resident variant)
+    static const int nw = [] { const char* e = getenv("BFE2_NW"); return e ? atoi(e) : 0; }();
+    if (nw == 3 && n > 30 && n <= 57) { *rpl = 19; *lpp = 3; return true; }
+    if (nw == 4 && n > 30 && n <= 60) { *rpl = 15; *lpp = 4; return true; }
     if (n <= 10) { *rpl = 5; *lpp = 2; return true; }
     if (n <= 30) { *rpl = 15; *lpp = 2; return true; }
     if (n <= 58) { *rpl = 29; *lpp = 2; return true; }
@@ -326,7 +330,7 @@ k_solve(PlanDev P, BatchArgs A) {
         double* s_W = smem + L.U;
         stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
         int sw;
-        if constexpr (REGS) sw = stage_jacobi_regs<RPL>(P, s_W, A.max_sweeps, tid);
+        if constexpr (REGS) sw = stage_jacobi_regs<RPL, LPP>(P, s_W, A.max_sweeps, tid);
         else sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
         if (sw < 0) info = -2;
         if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
@@ -358,6 +362,8 @@ int dispatch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
     // n <= 58: register-resident odd-even Jacobi (two warps per structure); BFE2_JACOBI=smem selects the
     // shared-memory round-robin variant for A/B measurements.  58 < n <= 116: shared-memory variant.
     static const bool use_smem = [] { const char* e = getenv("BFE2_JACOBI"); return e && !strcmp(e, "smem"); }();
+    if (plan->rpl == 19 && plan->lpp == 3) return launch_solve<19, 3, 96, 5, ASSEMBLE, true>(plan, A, stream);
+    if (plan->rpl == 15 && plan->lpp == 4) return launch_solve<15, 4, 128, 5, ASSEMBLE, true>(plan, A, stream);
     if (plan->lpp == 2 && !use_smem) {
         if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
         if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);

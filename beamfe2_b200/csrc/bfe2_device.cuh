@@ -51,7 +51,7 @@ __host__ __device__ inline SmemLayout make_layout(int nN, int nE, int n, int hbw
     L.invM = o;   o += n;
     o = (o + 1) & ~1;                                   // 16-byte align the big region
     L.U = o;
-    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 384) ? 384 : npad * LD);
+    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 640) ? 640 : npad * LD);
     L.lam = o;    o += npad;
     L.order = o;  o += (npad + 1) / 2 + 1;              // npad int32 + 2 flags, stored in double slots
     L.total = o;
@@ -640,9 +640,9 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
     sts_f64(pg_mine, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
 }
 
-template <int RPL>
+template <int RPL, int NW>
 __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
-    const int lane = tid & 31, h = tid >> 5;
+    const int lane = tid & 31, h = tid >> 5;          // h = row chunk owned by this warp, 0 .. NW-1
     const int npad = P.npad, LD = P.LD, NP = npad >> 1;
     const bool act = lane < NP;
     const bool last = lane == NP - 1;
@@ -659,15 +659,15 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
         }
     }
     __syncthreads();                                  // W is in registers: its memory becomes scratch
-    const unsigned pg0 = (unsigned)__cvta_generic_to_shared(s_W);      // [2 parity][2 warps][32 lanes]
-    const unsigned pg1 = pg0 + 64u * 8u;
-    const unsigned mine = 8u * (h * 32 + lane), w0 = 8u * lane, w1 = 8u * (32 + lane);
-    double* part_n = s_W + 128;                       // [2 warps][32 lanes][3]
+    const unsigned pg0 = (unsigned)__cvta_generic_to_shared(s_W);      // [2 parity][NW warps][32 lanes]
+    const unsigned pg1 = pg0 + NW * 32u * 8u;
+    const unsigned mine = 8u * (h * 32 + lane), w0 = 8u * lane;
+    double* part_n = s_W + 2 * NW * 32;               // [NW warps][32 lanes][3]
     int sweeps = 0;
     bool converged = false;
     for (; sweeps < max_sweeps; ++sweeps) {
         // refresh the cached squared norms from the data and form the first dot product of the sweep
-        double nA, nB, g;
+        double nA = 0.0, nB = 0.0, g = 0.0;
         {
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -684,18 +684,25 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
             part_n[(h * 32 + lane) * 3 + 1] = b0 + b1;
             part_n[(h * 32 + lane) * 3 + 2] = c0 + c1;
             __syncthreads();
-            nA = part_n[lane * 3] + part_n[(32 + lane) * 3];
-            nB = part_n[lane * 3 + 1] + part_n[(32 + lane) * 3 + 1];
-            g = part_n[lane * 3 + 2] + part_n[(32 + lane) * 3 + 2];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {            // same order in every warp: identical bits
+                nA += part_n[(w * 32 + lane) * 3];
+                nB += part_n[(w * 32 + lane) * 3 + 1];
+                g += part_n[(w * 32 + lane) * 3 + 2];
+            }
         }
         int rotated = 0;
         for (int step = 0; step < npad; step += 2) {
             jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, g, pg1 + mine, act, last, src_dn);
             __syncthreads();
-            g = lds_f64(pg1 + w0) + lds_f64(pg1 + w1);                 // same order in both warps: identical bits
+            g = lds_f64(pg1 + w0);
+#pragma unroll
+            for (int w = 1; w < NW; ++w) g += lds_f64(pg1 + w0 + 256u * w);
             jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, g, pg0 + mine, act, last, src_up);
             __syncthreads();
-            g = lds_f64(pg0 + w0) + lds_f64(pg0 + w1);
+            g = lds_f64(pg0 + w0);
+#pragma unroll
+            for (int w = 1; w < NW; ++w) g += lds_f64(pg0 + w0 + 256u * w);
         }
         if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
     }
