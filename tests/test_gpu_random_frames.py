@@ -1,0 +1,112 @@
+"""Randomised general frames (not chains): random connected topology on a jittered grid, random node numbering
+(wide bands -> warp band-Cholesky and generic substitution paths), several beams per node, random supports,
+nodal masses, nodal + uniform beam loads, n_free from 3 to 116 (both Jacobi variants, odd and even n).
+Everything is compared with the CPU oracle (numpy.linalg.solve / scipy.linalg.eigh on the same inputs)."""
+import numpy as np
+import pytest
+import torch
+
+from beamfe2_b200 import batch
+from beamfe2_b200.plan import Plan
+from oracle import beamfe2_oracle as orc
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+EPS = np.finfo(float).eps
+
+
+def random_frame(rng, n_nodes, extra_edges, n_clamped, n_pinned):
+    side = int(np.ceil(np.sqrt(n_nodes)))
+    pts = [(i, j) for i in range(side) for j in range(side)][:n_nodes]
+    xy = np.array(pts, dtype=float) * 1000.0 + rng.uniform(-200, 200, (n_nodes, 2))
+    perm = rng.permutation(n_nodes)                       # random numbering
+    xy = xy[perm]
+    edges = set()
+    order = rng.permutation(n_nodes)
+    for k in range(1, n_nodes):                           # random spanning tree: connected
+        a, b = int(order[k]), int(order[rng.integers(0, k)])
+        edges.add((min(a, b), max(a, b)))
+    while len(edges) < n_nodes - 1 + extra_edges:
+        a, b = (int(v) for v in rng.integers(0, n_nodes, 2))
+        if a != b:
+            edges.add((min(a, b), max(a, b)))
+    conn = np.array(sorted(edges), dtype=np.int32)
+    conn = conn[rng.permutation(len(conn))]
+    flip = rng.uniform(size=len(conn)) < 0.5              # beam direction i -> j either way
+    conn[flip] = conn[flip][:, ::-1]
+    nodes = rng.permutation(n_nodes)
+    fixed = []
+    for k in nodes[:n_clamped]:
+        fixed += [3 * k, 3 * k + 1, 3 * k + 2]
+    for k in nodes[n_clamped:n_clamped + n_pinned]:
+        fixed += [3 * k, 3 * k + 1]
+    return xy, conn, sorted(int(f) for f in fixed)
+
+
+CASES = [(2, 0, 1, 0), (3, 0, 1, 0), (4, 1, 1, 1), (6, 2, 1, 1), (9, 3, 2, 0), (12, 4, 1, 2), (16, 6, 2, 1),
+         (20, 8, 1, 0), (21, 5, 1, 1), (25, 10, 2, 2), (30, 12, 2, 0), (36, 14, 2, 3), (40, 16, 1, 1)]
+
+
+@pytest.mark.parametrize('n_nodes,extra,n_cl,n_pin', CASES)
+def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin):
+    rng = np.random.default_rng(1000 * n_nodes + extra)
+    xy, conn, fixed = random_frame(rng, n_nodes, extra, n_cl, n_pin)
+    nE = len(conn)
+    n_free = 3 * n_nodes - len(fixed)
+    if n_free > 116:
+        pytest.skip('beyond the shared-memory Jacobi path')
+    B, C = 5, 2
+    coords = xy[None] + rng.uniform(-20, 20, (B, n_nodes, 2))
+    props = np.stack([rng.uniform(1.9e5, 2.2e5, (B, nE)), rng.uniform(2e3, 2e4, (B, nE)),
+                      rng.uniform(1e6, 1e8, (B, nE)), rng.uniform(7e-9, 8.5e-9, (B, nE))], axis=-1)
+    lumped = rng.uniform(size=nE) < 0.0                   # consistent mass (the lumped matrix is ill-posed)
+    mass = rng.uniform(0, 1e-3, (B, n_nodes, 2)) * (rng.uniform(size=(1, n_nodes, 1)) < 0.3)
+    f_nodal = rng.uniform(-1e4, 1e4, (B, C, 3 * n_nodes)) * (rng.uniform(size=(1, C, 3 * n_nodes)) < 0.2)
+    f_nodal[:, :, 0] += 1.0                               # never an all-zero case
+    L, _ = orc.length_direction(coords, conn)
+    q = rng.uniform(-5, 5, (B, C, nE)) * (rng.uniform(size=(1, C, nE)) < 0.4)
+    Lc = np.broadcast_to(L[:, None, :], q.shape)
+    r_local = np.zeros((B, C, nE, 6))                     # Loads.py:264-270
+    r_local[..., 1] = q * Lc / 2
+    r_local[..., 2] = q * (Lc ** 2) / 12
+    r_local[..., 4] = q * Lc / 2
+    r_local[..., 5] = -1 * q * (Lc ** 2) / 12.
+    plan = Plan(n_nodes, conn, fixed, lumped)
+    assert plan.n_free == n_free
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)     # noqa: E731
+    if plan.smem_bytes(C) > 227 * 1024:                   # wide band AND large n: loud refusal, not a wrong answer
+        with pytest.raises(Exception, match='shared memory'):
+            batch.solve_fused(plan, T(coords), T(props), T(mass), T(f_nodal), T(r_local), n_modes=4)
+        return
+    out = batch.solve_fused(plan, T(coords), T(props), T(mass), T(f_nodal), T(r_local), n_modes=min(n_free, 8))
+    assert (out['info'] == 0).all(), out['info']
+    o = orc.solve_batch(conn, fixed, coords, props, mass, f_nodal, r_local, lumped, n_modes=min(n_free, 8))
+    # band width claim and unfused assembly
+    Kb, Mb = batch.assemble_banded(plan, T(coords), T(props), T(mass))
+    for b in range(B):
+        assert util.relmax(np.tril(plan.band_to_dense(Kb[b].cpu().numpy())), np.tril(o['Kc'][b])) < 1e-14
+        assert util.relmax(np.tril(plan.band_to_dense(Mb[b].cpu().numpy())), np.tril(o['Mc'][b])) < 1e-14
+    condK = np.linalg.cond(o['Kc']).max()
+    tol_s = max(1e-10, 50 * EPS * condK)                  # both solvers are backward stable: forward error ~ eps cond
+    for b in range(B):
+        assert util.relmax(out['u'][b].cpu().numpy(), o['u'][b]) < tol_s
+        assert util.relmax(out['endforces'][b].cpu().numpy(), o['endforces'][b]) < tol_s
+        assert util.relmax(out['reactions'][b].cpu().numpy(), o['reactions'][b]) < tol_s
+    # equilibrium at the free DOFs: reactions vanish there
+    free = torch.as_tensor(plan.pos_of_free.astype(np.int64), device=DEV)
+    react = out['reactions']
+    assert (react[:, :, free].abs().amax() / react.abs().amax()).item() < max(1e-9, 50 * EPS * condK)
+    lam = out['lam'].cpu().numpy()
+    bound = 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']
+    assert (np.abs(lam / o['lam'] - 1) < bound).all()
+    phi = out['phi'].cpu().numpy()
+    keep = plan.pos_of_free
+    for b in range(B):
+        Pf = phi[b][:, keep]
+        assert np.abs(Pf @ o['Mc'][b] @ Pf.T - np.eye(Pf.shape[0])).max() < 1e-9
+        res = o['Kc'][b] @ Pf.T - (o['Mc'][b] @ Pf.T) * lam[b, None, :Pf.shape[0]]
+        assert (np.abs(res).max(axis=0) / (np.abs(o['Kc'][b]).max() * np.abs(Pf).max(axis=1))).max() < 1e-11
+    gap = np.minimum(np.diff(o['lam'], axis=1, prepend=-np.inf), np.diff(o['lam'], axis=1, append=np.inf))[:, :phi.shape[1]]
+    tol_v = 1e-10 + 256 * EPS * o['lam'][:, -1:] / gap
+    assert (util.mode_err(phi, o['phi']) < tol_v).all()
