@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get('BFE2_LIB', os.path.join(_HERE, 'libbfe2.so'))   # BFE
 # every symbol include/bfe2.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     'bfe2_version', 'bfe2_last_error', 'bfe2_device_count',
-    'bfe2_plan_create', 'bfe2_plan_destroy', 'bfe2_plan_dims', 'bfe2_plan_get_array',
+    'bfe2_plan_create', 'bfe2_plan_create_ex', 'bfe2_plan_destroy', 'bfe2_plan_dims', 'bfe2_plan_get_array',
     'bfe2_plan_smem_bytes', 'bfe2_workspace_bytes',
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
     'bfe2_solve_fused',
@@ -58,6 +58,8 @@ def lib():
     L.bfe2_device_count.restype = C.c_int
     L.bfe2_plan_create.restype = C.c_int
     L.bfe2_plan_create.argtypes = [C.POINTER(vp), i32, i32, vp, i32, vp, vp]
+    L.bfe2_plan_create_ex.restype = C.c_int
+    L.bfe2_plan_create_ex.argtypes = [C.POINTER(vp), i32, i32, vp, i32, vp, vp, i32]
     L.bfe2_plan_destroy.restype = None
     L.bfe2_plan_destroy.argtypes = [vp]
     L.bfe2_plan_dims.restype = C.c_int

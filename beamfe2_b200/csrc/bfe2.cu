@@ -81,6 +81,54 @@ bool jacobi_config(int n, int* rpl, int* lpp) {
     return false;
 }
 
+// Reverse Cuthill-McKee ordering of the node graph (beams = edges): returns the nodes in their new order.
+std::vector<int> rcm_node_order(int n_nodes, int n_elem, const int32_t* conn) {
+    std::vector<std::vector<int>> adj(n_nodes);
+    for (int e = 0; e < n_elem; ++e) {
+        adj[conn[2 * e]].push_back(conn[2 * e + 1]);
+        adj[conn[2 * e + 1]].push_back(conn[2 * e]);
+    }
+    for (auto& a : adj) {
+        std::sort(a.begin(), a.end());
+        a.erase(std::unique(a.begin(), a.end()), a.end());
+    }
+    std::vector<int> order;
+    std::vector<char> seen(n_nodes, 0);
+    while ((int)order.size() < n_nodes) {
+        int start = -1;                                 // unvisited node of minimum degree
+        for (int k = 0; k < n_nodes; ++k)
+            if (!seen[k] && (start < 0 || adj[k].size() < adj[start].size())) start = k;
+        size_t head = order.size();
+        order.push_back(start);
+        seen[start] = 1;
+        while (head < order.size()) {
+            const int u = order[head++];
+            std::vector<int> nb;
+            for (int v : adj[u])
+                if (!seen[v]) { nb.push_back(v); seen[v] = 1; }
+            std::sort(nb.begin(), nb.end(), [&](int a, int b) {
+                return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b;
+            });
+            order.insert(order.end(), nb.begin(), nb.end());
+        }
+    }
+    std::reverse(order.begin(), order.end());
+    return order;
+}
+
+int half_bandwidth(const bfe2_plan* p, const int32_t* conn) {
+    int hbw = 0;
+    for (int e = 0; e < p->nE; ++e) {
+        int lo = 1 << 30, hi = -1;
+        for (int a = 0; a < 6; ++a) {
+            const int f = p->free_of_pos[3 * conn[2 * e + a / 3] + a % 3];
+            if (f >= 0) { lo = std::min(lo, f); hi = std::max(hi, f); }
+        }
+        if (hi >= 0) hbw = std::max(hbw, hi - lo);
+    }
+    return hbw;
+}
+
 int plan_upload(bfe2_plan* p) {
     int dev = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
@@ -395,6 +443,11 @@ int bfe2_device_count(void) {
 
 int bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int32_t* conn,
                      int32_t n_fixed, const int32_t* fixed_pos, const uint8_t* lumped) {
+    return bfe2_plan_create_ex(out, n_nodes, n_elem, conn, n_fixed, fixed_pos, lumped, 0);
+}
+
+int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int32_t* conn,
+                        int32_t n_fixed, const int32_t* fixed_pos, const uint8_t* lumped, int32_t flags) {
     if (!out) return fail(-1, "out is NULL");
     *out = nullptr;
     if (n_nodes < 2 || n_elem < 1 || !conn) return fail(-1, "need at least 2 nodes and 1 beam");
@@ -432,14 +485,22 @@ int bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int
     // n == 0 (every DOF supported, e.g. the clamped-clamped element of Tests/test_internal_beamloads.py)
     // is legal for the static path: u = 0, end forces = -r_local.  The modal path is refused.
     // half bandwidth in free numbering
-    p->hbw = 0;
-    for (int e = 0; e < n_elem; ++e) {
-        int lo = 1 << 30, hi = -1;
-        for (int a = 0; a < 6; ++a) {
-            const int f = p->free_of_pos[3 * conn[2 * e + a / 3] + a % 3];
-            if (f >= 0) { lo = std::min(lo, f); hi = std::max(hi, f); }
-        }
-        if (hi >= 0) p->hbw = std::max(p->hbw, hi - lo);
+    p->hbw = half_bandwidth(p, conn);
+    if ((flags & BFE2_PLAN_REORDER) && p->n > 0) {
+        // internal bandwidth-reducing renumbering of the FREE DOFs (reverse Cuthill-McKee on the node graph, the
+        // DOFs of a node stay together).  Purely internal: inputs and outputs keep the reference's positions
+        // (Structure.py:379-393) because every kernel goes through free_of_pos / pos_of_free.
+        std::vector<int32_t> fop(p->sumdof, -1), pof;
+        for (int f : p->fixed) fop[f] = -2;
+        for (int node : rcm_node_order(n_nodes, n_elem, conn))
+            for (int k = 0; k < 3; ++k)
+                if (fop[3 * node + k] != -2) { fop[3 * node + k] = (int32_t)pof.size(); pof.push_back(3 * node + k); }
+        for (int f : p->fixed) fop[f] = -1;
+        bfe2_plan trial;
+        trial.nE = p->nE;
+        trial.free_of_pos = fop;
+        const int hb2 = half_bandwidth(&trial, conn);
+        if (hb2 < p->hbw) { p->free_of_pos = fop; p->pos_of_free = pof; p->hbw = hb2; }
     }
     p->nslots = (p->hbw + 1) * p->n;
     // scatter plan: slot (d, j) <- e*36 + r*6 + c for every lower-triangle contribution, beam order

@@ -40,7 +40,7 @@ def positions_to_eliminate(supports: dict) -> list:
 class Plan:
     """Owns a bfe2_plan handle.  conn: [nE,2] 0-based node indices in beam-list order."""
 
-    def __init__(self, n_nodes: int, conn, fixed_positions, lumped=None):
+    def __init__(self, n_nodes: int, conn, fixed_positions, lumped=None, reorder: bool = False):
         L = _lib.lib()
         conn = np.ascontiguousarray(np.asarray(conn, dtype=np.int32).reshape(-1, 2))
         fixed = np.ascontiguousarray(np.asarray(list(fixed_positions), dtype=np.int32).ravel())
@@ -49,9 +49,9 @@ class Plan:
             lump = np.ascontiguousarray(np.asarray(lumped, dtype=np.uint8).ravel())
             assert lump.shape[0] == conn.shape[0]
         h = C.c_void_p()
-        _lib.check(L.bfe2_plan_create(C.byref(h), int(n_nodes), int(conn.shape[0]), _lib.ptr(conn),
-                                      int(fixed.shape[0]), _lib.ptr(fixed) if fixed.size else None,
-                                      _lib.ptr(lump)))
+        _lib.check(L.bfe2_plan_create_ex(C.byref(h), int(n_nodes), int(conn.shape[0]), _lib.ptr(conn),
+                                         int(fixed.shape[0]), _lib.ptr(fixed) if fixed.size else None,
+                                         _lib.ptr(lump), 1 if reorder else 0))
         self._h = h
         d = [C.c_int32() for _ in range(6)]
         _lib.check(L.bfe2_plan_dims(h, *[C.byref(x) for x in d]))
@@ -60,8 +60,8 @@ class Plan:
         self.lumped = lump
 
     @classmethod
-    def from_supports(cls, n_nodes, conn, supports: dict, lumped=None):
-        return cls(n_nodes, conn, positions_to_eliminate(supports), lumped)
+    def from_supports(cls, n_nodes, conn, supports: dict, lumped=None, reorder: bool = False):
+        return cls(n_nodes, conn, positions_to_eliminate(supports), lumped, reorder)
 
     @property
     def handle(self):

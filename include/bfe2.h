@@ -79,6 +79,12 @@ int  bfe2_plan_create(bfe2_plan** out, int32_t n_nodes, int32_t n_elem,
                       const int32_t* conn /*[nE,2] 0-based*/,
                       int32_t n_fixed, const int32_t* fixed_pos /* any order, no duplicates */,
                       const uint8_t* lumped /*[nE] or NULL*/);
+/* flags: BFE2_PLAN_REORDER = internal bandwidth-reducing (reverse Cuthill-McKee) numbering of the free DOFs for
+ * frames that are not numbered as chains (e.g. Examples/Chopra_105.py:35-45); inputs and outputs keep the
+ * reference's DOF positions, only the band storage [B, hbw+1, n] is in the internal order. */
+#define BFE2_PLAN_REORDER 1
+int  bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const int32_t* conn,
+                         int32_t n_fixed, const int32_t* fixed_pos, const uint8_t* lumped, int32_t flags);
 void bfe2_plan_destroy(bfe2_plan* plan);
 int  bfe2_plan_dims(const bfe2_plan* plan, int32_t* n_nodes, int32_t* n_elem, int32_t* sumdof,
                     int32_t* n_free, int32_t* hbw, int32_t* n_contrib);

@@ -48,8 +48,9 @@ CASES = [(2, 0, 1, 0), (3, 0, 1, 0), (4, 1, 1, 1), (6, 2, 1, 1), (9, 3, 2, 0), (
          (20, 8, 1, 0), (21, 5, 1, 1), (25, 10, 2, 2), (30, 12, 2, 0), (36, 14, 2, 3), (40, 16, 1, 1)]
 
 
+@pytest.mark.parametrize('reorder', [False, True])
 @pytest.mark.parametrize('n_nodes,extra,n_cl,n_pin', CASES)
-def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin):
+def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin, reorder):
     rng = np.random.default_rng(1000 * n_nodes + extra)
     xy, conn, fixed = random_frame(rng, n_nodes, extra, n_cl, n_pin)
     nE = len(conn)
@@ -72,8 +73,13 @@ def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin):
     r_local[..., 2] = q * (Lc ** 2) / 12
     r_local[..., 4] = q * Lc / 2
     r_local[..., 5] = -1 * q * (Lc ** 2) / 12.
-    plan = Plan(n_nodes, conn, fixed, lumped)
+    plan = Plan(n_nodes, conn, fixed, lumped, reorder=reorder)     # reorder: internal RCM numbering of the free DOFs
     assert plan.n_free == n_free
+    keep_sorted = orc.free_positions(n_nodes, fixed)
+    assert sorted(plan.pos_of_free.tolist()) == keep_sorted.tolist()
+    perm = np.searchsorted(keep_sorted, plan.pos_of_free)           # internal free index -> ascending free index
+    if not reorder:
+        assert np.array_equal(perm, np.arange(n_free))
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)     # noqa: E731
     if plan.smem_bytes(C) > 227 * 1024:                   # wide band AND large n: loud refusal, not a wrong answer
         with pytest.raises(Exception, match='shared memory'):
@@ -85,8 +91,9 @@ def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin):
     # band width claim and unfused assembly
     Kb, Mb = batch.assemble_banded(plan, T(coords), T(props), T(mass))
     for b in range(B):
-        assert util.relmax(np.tril(plan.band_to_dense(Kb[b].cpu().numpy())), np.tril(o['Kc'][b])) < 1e-14
-        assert util.relmax(np.tril(plan.band_to_dense(Mb[b].cpu().numpy())), np.tril(o['Mc'][b])) < 1e-14
+        Kp, Mp = o['Kc'][b][np.ix_(perm, perm)], o['Mc'][b][np.ix_(perm, perm)]
+        assert util.relmax(np.tril(plan.band_to_dense(Kb[b].cpu().numpy())), np.tril(Kp)) < 1e-14
+        assert util.relmax(np.tril(plan.band_to_dense(Mb[b].cpu().numpy())), np.tril(Mp)) < 1e-14
     condK = np.linalg.cond(o['Kc']).max()
     tol_s = max(1e-10, 50 * EPS * condK)                  # both solvers are backward stable: forward error ~ eps cond
     for b in range(B):
@@ -94,14 +101,14 @@ def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin):
         assert util.relmax(out['endforces'][b].cpu().numpy(), o['endforces'][b]) < tol_s
         assert util.relmax(out['reactions'][b].cpu().numpy(), o['reactions'][b]) < tol_s
     # equilibrium at the free DOFs: reactions vanish there
-    free = torch.as_tensor(plan.pos_of_free.astype(np.int64), device=DEV)
+    free = torch.as_tensor(keep_sorted.astype(np.int64), device=DEV)
     react = out['reactions']
     assert (react[:, :, free].abs().amax() / react.abs().amax()).item() < max(1e-9, 50 * EPS * condK)
     lam = out['lam'].cpu().numpy()
     bound = 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']
     assert (np.abs(lam / o['lam'] - 1) < bound).all()
     phi = out['phi'].cpu().numpy()
-    keep = plan.pos_of_free
+    keep = keep_sorted
     for b in range(B):
         Pf = phi[b][:, keep]
         assert np.abs(Pf @ o['Mc'][b] @ Pf.T - np.eye(Pf.shape[0])).max() < 1e-9
