@@ -176,7 +176,7 @@ class HostPipeline:
     IN_KEYS = ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')
     OUT_KEYS = ('u', 'endforces', 'reactions', 'lam', 'phi', 'info', 'sweeps')
 
-    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, chunk: int = 16384, n_streams: int = 3,
+    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, chunk: int = 4096, n_streams: int = 3,
                  device=None, modal: bool = True):
         self.plan, self.C, self.modal = plan, int(n_loadcases), bool(modal)
         self.n_modes = int(n_modes) if modal else 0

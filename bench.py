@@ -327,7 +327,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=100000, help='structure variants per GPU per step')
-    ap.add_argument('--chunk', type=int, default=12500, help='HostPipeline chunk (structures)')
+    ap.add_argument('--chunk', type=int, default=3125, help='HostPipeline chunk (structures)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=16384, help='CPU oracle: variants per worker')
     ap.add_argument('--no-cpu', action='store_true')
