@@ -1,7 +1,7 @@
 """Pins the CPU oracle (oracle/beamfe2_oracle.py) to the reference:
    (1) every golden case produced by the REAL reference (tests/golden, made by oracle/make_golden.py),
    (2) the reference's own known-answer tests, restated here with their file:line,
-   (3) live against /root/reference when it is present (build container only)."""
+   (3) live against the reference checkout when it is present (build container only; CPU test)."""
 import math
 
 import numpy as np
