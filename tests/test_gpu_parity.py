@@ -345,3 +345,29 @@ def test_large_batch_properties():
     # trace identity: sum of all eigenvalues == trace(M^-1 K)
     tr = torch.linalg.solve(Md, Kd).diagonal(dim1=1, dim2=2).sum(dim=1)
     assert ((lam[sub].sum(dim=1) / tr) - 1).abs().max() < 1e-10
+
+
+def test_degenerate_eigenvalues_subspace():
+    """Two identical, disconnected cantilevers in one structure: every eigenvalue is exactly double.  Mode shapes
+    of a cluster are only defined up to a rotation inside the eigenspace, so they are compared by projector."""
+    nE = 6
+    xy = np.array([(k * 100.0, 0.0) for k in range(nE + 1)] + [(k * 100.0, 500.0) for k in range(nE + 1)])
+    conn = np.array([[k, k + 1] for k in range(nE)] + [[nE + 1 + k, nE + 2 + k] for k in range(nE)], dtype=np.int32)
+    fixed = [0, 1, 2, 3 * (nE + 1), 3 * (nE + 1) + 1, 3 * (nE + 1) + 2]
+    props = np.tile(np.array([2.1e5, 30.0, 22.5, 7.85e-9]), (2 * nE, 1))
+    plan = Plan(2 * (nE + 1), conn, fixed)
+    n = plan.n_free
+    out = batch.solve_fused(plan, T(xy[None]), T(props[None]), None, None, None, n_modes=n)
+    assert int(out['info'][0]) == 0
+    lam = out['lam'][0].cpu().numpy()
+    phi = out['phi'][0].cpu().numpy()
+    o = orc.solve_batch(conn, fixed, xy, props, nodal_mass=np.zeros((2 * (nE + 1), 2)))
+    assert np.abs(lam / o['lam'] - 1).max() < 1e-10 + 64 * EPS * o['lam'][-1] / o['lam'][0]
+    assert np.abs(lam[0::2] / lam[1::2] - 1).max() < 1e-11          # exact pairs
+    keep = plan.pos_of_free
+    Pg, Ps, M = phi[:, keep], o['phi'][:, keep], o['Mc']
+    assert np.abs(Pg @ M @ Pg.T - np.eye(n)).max() < 1e-9
+    for k in range(0, 8, 2):                                           # projector onto each 2-dimensional eigenspace
+        Pr_g = Pg[k:k + 2].T @ Pg[k:k + 2] @ M
+        Pr_s = Ps[k:k + 2].T @ Ps[k:k + 2] @ M
+        assert np.abs(Pr_g - Pr_s).max() < 1e-8
