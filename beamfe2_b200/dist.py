@@ -34,6 +34,46 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host buffers are
+    allocated (first touch places them on that node).  With one process per GPU the host side of the
+    end-to-end path (H2D / D2H through pinned memory) otherwise crosses the socket interconnect.
+    Returns the node id or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:
+            return None
+    try:
+        bus = str(bus).lower()
+        if bus.count(':') == 2 and len(bus.split(':')[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open('/sys/bus/pci/devices/%s/numa_node' % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def summarize(u, lam, info, n_freq=3):
     """Per-structure summary [B, 2 + n_freq]: info, max |u| over load cases and DOFs, first circular
     frequencies.  ~40 B per structure -- this is all that ever crosses NVLink."""

@@ -201,6 +201,7 @@ def run_gpu_arm(args):
             print('bench.py: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE' % (world, args.gpus), file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bdist.bind_to_gpu_numa_node(local) if world > 1 else None
     B = args.batch
     conn, sup = sweep.p20_topology()
     plan = Plan.from_supports(21, conn, sup)
@@ -295,7 +296,7 @@ def run_gpu_arm(args):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': bi * B, 'd2h_bytes_per_step': bo * B,
                 'ms_per_step': e2e_ms, 'wall_ms_per_step': e2e_wall * 1e3, 'chunk': args.chunk,
-                'matches_device_run': e2e_ok},
+                'matches_device_run': e2e_ok, 'numa_node': numa},
         'gpu_launches': args.steps,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
