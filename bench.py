@@ -300,7 +300,7 @@ def run_gpu_arm(args):
         'gpu_launches': args.steps,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-                     'kernel': 'k_solve<29,2,64,6,true> (fused K1->K4)', 'kernel_ms': kernel_ms,
+                     'kernel': 'k_solve<29,2,64,5,true,true> (fused K1->K4)', 'kernel_ms': kernel_ms,
                      'algorithmic_bytes_per_structure': ALGO_BYTES_PER_STRUCT,
                      'note': 'the fused kernel is FP64/shared-memory bound, not HBM bound (SURVEY 8d); see fp64',
                      'fp64': {'achieved_tflops': fp64_ach, 'peak_tflops_measured_dfma': fp64_peak,
