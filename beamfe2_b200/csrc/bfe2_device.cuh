@@ -614,9 +614,10 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
         nB += tg;
         rotated = 1;
     }
-    double acc[8];
+    constexpr int NACC = 2;      // accumulators of the fused dot product (measured: 2 > 4 > 8, register pressure)
+    double acc[NACC];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     if (__any_sync(0xffffffffu, rot || (ODD && last && act))) {
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
@@ -625,19 +626,19 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
             const double na = fma(c, A[r], -sb);
             if (!ODD) { A[r] = na; B[r] = __shfl_sync(0xffffffffu, nb, src); }
             else { B[r] = nb; A[r] = __shfl_sync(0xffffffffu, na, src); }
-            acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
+            acc[r & (NACC - 1)] = fma(A[r], B[r], acc[r & (NACC - 1)]);
         }
     } else {                                          // nobody in this warp rotates: move and multiply only
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             if (!ODD) B[r] = __shfl_sync(0xffffffffu, B[r], src);
             else A[r] = __shfl_sync(0xffffffffu, A[r], src);
-            acc[r & 7] = fma(A[r], B[r], acc[r & 7]);
+            acc[r & (NACC - 1)] = fma(A[r], B[r], acc[r & (NACC - 1)]);
         }
     }
     if (!ODD) nB = __shfl_sync(0xffffffffu, nB, src);
     else nA = __shfl_sync(0xffffffffu, nA, src);
-    sts_f64(pg_mine, ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
+    sts_f64(pg_mine, acc[0] + acc[1]);
 }
 
 template <int RPL, int NW>
@@ -692,6 +693,7 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
             }
         }
         int rotated = 0;
+#pragma unroll 1
         for (int step = 0; step < npad; step += 2) {
             jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, g, pg1 + mine, act, last, src_dn);
             __syncthreads();
