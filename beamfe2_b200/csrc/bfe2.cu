@@ -263,29 +263,81 @@ k_element_km(long long nE, const double* __restrict__ xi, const double* __restri
     }
 }
 
-// ---- K2: assembly only: bands to HBM ----------------------------------------------------------
-__global__ void __launch_bounds__(64)
-k_assemble(PlanDev P, BatchArgs A) {
+// ---- K2: WARP-PER-STRUCTURE assembly: bands to HBM.  The integer plan is cached once per block in shared
+//      memory (blocks are persistent: grid-stride over structures), every warp stages its structure's inputs
+//      and the 2 x nE element matrices in its own shared-memory slice, then each lane owns band slots
+//      lane, lane+32, ... and adds their contributions in beam order (no atomics); the sums go straight to HBM
+//      as coalesced 8-byte stores.  Only __syncwarp inside the loop.
+constexpr int K2_WARPS = 8;
+
+__global__ void __launch_bounds__(K2_WARPS * 32)
+k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
     extern __shared__ __align__(16) double smem[];
-    const SmemLayout L = make_layout(P.nN, P.nE, P.n, P.hbw, P.npad, P.LD, 0);
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mass = A.Mb_out != nullptr;
-    for (long long b = blockIdx.x; b < A.B; b += gridDim.x) {
-        copy_in(smem + L.coords, A.coords + b * 2 * P.nN, 2 * P.nN, tid, nt);
-        copy_in(smem + L.props, A.props + b * 4 * P.nE, 4 * P.nE, tid, nt);
-        if (A.nodal_mass != nullptr) copy_in(smem + L.mass, A.nodal_mass + b * 2 * P.nN, 2 * P.nN, tid, nt);
-        __syncthreads();
-        stage_elements(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 36 * P.nE,
-                       want_mass, tid, nt);
-        __syncthreads();
-        stage_assemble(P, smem + L.U, smem + L.U + 36 * P.nE, A.nodal_mass ? smem + L.mass : nullptr,
-                       smem + L.Kb, smem + L.Mb, want_mass, tid, nt);
-        __syncthreads();
-        for (int i = tid; i < P.nslots; i += nt) {
-            A.Kb_out[b * P.nslots + i] = smem[L.Kb + i];
-            if (want_mass) A.Mb_out[b * P.nslots + i] = smem[L.Mb + i];
+    // block-shared plan cache (int32)
+    const int per_warp = 4 * P.nN + 4 * P.nE + 72 * P.nE;                 // doubles
+    const int nw = blockDim.x >> 5;                                        // warps (= structures in flight) per block
+    int* c_conn = reinterpret_cast<int*>(smem + (size_t)nw * per_warp);
+    int* c_pos = c_conn + 2 * P.nE;
+    int* c_ptr = c_pos + P.n;
+    int* c_con = c_ptr + P.nslots + 1;
+    int* c_lump = c_con + ncontrib;
+    for (int i = tid; i < 2 * P.nE; i += blockDim.x) c_conn[i] = P.conn[i];
+    for (int i = tid; i < P.n; i += blockDim.x) c_pos[i] = P.pos_of_free[i];
+    for (int i = tid; i <= P.nslots; i += blockDim.x) c_ptr[i] = P.slot_ptr[i];
+    for (int i = tid; i < ncontrib; i += blockDim.x) c_con[i] = P.contrib[i];
+    for (int i = tid; i < P.nE; i += blockDim.x) c_lump[i] = P.lumped[i];
+    __syncthreads();
+    double* w_coords = smem + (size_t)warp * per_warp;
+    double* w_props = w_coords + 2 * P.nN;
+    double* w_mass = w_props + 4 * P.nE;
+    double* w_Ke = w_mass + 2 * P.nN;
+    double* w_Me = w_Ke + 36 * P.nE;
+    const long long nwarps = (long long)gridDim.x * nw;
+    for (long long b = (long long)blockIdx.x * nw + warp; b < A.B; b += nwarps) {
+        for (int i = lane; i < 2 * P.nN; i += 32) w_coords[i] = A.coords[b * 2 * P.nN + i];
+        for (int i = lane; i < 4 * P.nE; i += 32) w_props[i] = A.props[b * 4 * P.nE + i];
+        if (A.nodal_mass != nullptr)
+            for (int i = lane; i < 2 * P.nN; i += 32) w_mass[i] = A.nodal_mass[b * 2 * P.nN + i];
+        __syncwarp();
+        const int items = want_mass ? 2 * P.nE : P.nE;
+        for (int it = lane; it < items; it += 32) {
+            const int e = it < P.nE ? it : it - P.nE;
+            const bool mass = it >= P.nE;
+            const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
+            double L, c, s;
+            beam_geometry(w_coords[2 * ni], w_coords[2 * ni + 1], w_coords[2 * nj], w_coords[2 * nj + 1], L, c, s);
+            double X[6][6];
+            if (!mass) ke_local(X, w_props[4 * e], w_props[4 * e + 1], w_props[4 * e + 2], L);
+            else me_local(X, w_props[4 * e + 3], w_props[4 * e + 1], L, c_lump[e] != 0);
+            rotate_to_global(X, c, s);
+            double* dst = (mass ? w_Me : w_Ke) + 36 * e;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) dst[6 * r + q] = X[r][q];
         }
-        __syncthreads();
+        __syncwarp();
+        for (int slot = lane; slot < P.nslots; slot += 32) {
+            const int p0 = c_ptr[slot], p1 = c_ptr[slot + 1];
+            double k = 0.0, m = 0.0;
+            for (int p = p0; p < p1; ++p) {
+                const int idx = c_con[p];
+                k += w_Ke[idx];
+                if (want_mass) m += w_Me[idx];
+            }
+            A.Kb_out[b * P.nslots + slot] = k;
+            if (want_mass) {
+                if (slot < P.n && A.nodal_mass != nullptr) {
+                    const int pos = c_pos[slot];
+                    const int dof = pos % 3;
+                    if (dof < 2) m += w_mass[2 * (pos / 3) + dof];
+                }
+                A.Mb_out[b * P.nslots + slot] = m;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -616,17 +668,20 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     if (int r = plan_upload(plan)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
-    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, 0);
-    const size_t bytes = (size_t)L.total * sizeof(double);
+    const size_t per_warp = (size_t)(4 * plan->nN + 4 * plan->nE + 72 * plan->nE) * sizeof(double);
+    const size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + plan->ncontrib + plan->nE) * sizeof(int) + 16;
+    int nw = K2_WARPS;                                 // fewer warps per block when a structure's slice is large
+    while (nw > 1 && nw * per_warp + cache > 110 * 1024) --nw;
+    const size_t bytes = nw * per_warp + cache;
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
     BFE2_CUDA(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     int dev = 0, sms = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
     BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)std::min<long long>(B, (long long)sms * 16);
-    PlanDev P = plan->dev;
-    P.npad = 0; P.LD = 0;                              // no Jacobi region needed
-    k_assemble<<<grid, 64, bytes, (cudaStream_t)stream>>>(P, A);
+    const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
+    const long long want = (B + nw - 1) / nw;
+    const int grid = (int)std::min<long long>(want, (long long)sms * resident);
+    k_assemble<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(plan->dev, A, plan->ncontrib);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
