@@ -79,3 +79,54 @@ class BucklingSolver(Solver):
 
     def solve(self):
         raise NotImplementedError('linear buckling is not part of the accelerated path')
+
+
+def solve_structures(structures, static=True, modal=True):
+    """Solve MANY drop-in Structures that share one topology (same beams / node numbering / supports / mass-matrix
+    flags, different coordinates, sections, masses and loads) in ONE fused launch, and fill every
+    structure.results[...] exactly as the per-structure solvers do.  Returns a list of (static_ok, modal_ok).
+    This is the batch axis the reference does not have (it would loop over Solver.solve())."""
+    import torch
+    from . import batch
+    if not structures:
+        return []
+    packs = [st.pack() for st in structures]
+    plan0, pk0 = packs[0]
+    for plan, pk in packs[1:]:
+        same = (plan.n_nodes == plan0.n_nodes and plan.n_elem == plan0.n_elem and np.array_equal(plan.conn, plan0.conn)
+                and np.array_equal(plan.fixed, plan0.fixed) and np.array_equal(plan.lumped, plan0.lumped))
+        if not same:
+            raise ValueError('solve_structures: all structures must share one topology plan')
+
+    def dev(key):
+        return torch.as_tensor(np.ascontiguousarray(np.stack([pk[key] for _, pk in packs])), dtype=torch.float64,
+                               device='cuda')
+    has_load = [st._load_vector is not None and np.count_nonzero(st._load_vector) != 0 for st in structures]
+    has_mass = [np.count_nonzero(pk['props'][:, 3] * pk['props'][:, 1]) != 0 or np.count_nonzero(pk['nodal_mass']) != 0
+                for _, pk in packs]
+    do_static = static and any(has_load)
+    do_modal = modal and plan0.n_free > 0 and any(has_mass)
+    if not (do_static or do_modal):
+        return [(False, False)] * len(structures)
+    out = batch.solve_fused(plan0, dev('coords'), dev('props'), dev('nodal_mass') if do_modal else None,
+                            dev('f_nodal') if do_static else None, dev('r_local') if do_static else None,
+                            modal=do_modal, n_modes=plan0.n_free if do_modal else 0)
+    torch.cuda.synchronize()
+    host = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    flags = []
+    for b, st in enumerate(structures):
+        info = int(host['info'][b])
+        s_ok = m_ok = False
+        if do_static and has_load[b] and info <= 0:
+            st.results['linear static'] = Results.LinearStaticResult(
+                structure=st, displacements=[np.matrix(host['u'][b, 0]).T], endforces=host['endforces'][b, 0],
+                reactions=host['reactions'][b, 0])
+            st.results['linear static'].solved = s_ok = True
+        if do_modal and has_mass[b] and info == 0:
+            lam = host['lam'][b]
+            st.results['modal'] = Results.ModalResult(
+                structure=st, circular_freq=[math.sqrt(x) for x in lam if x > 0],
+                modalshapes=[np.matrix(host['phi'][b, k]).T for k in range(host['phi'].shape[1])])
+            st.results['modal'].solved = m_ok = True
+        flags.append((s_ok, m_ok))
+    return flags

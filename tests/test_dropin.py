@@ -246,3 +246,27 @@ def test_modal_returns_false_without_mass():
     b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=1., I=1., A=1., rho=0.)
     s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
     assert s.solver['modal'].solve() is False and not s.results['modal'].solved
+
+
+@gpu
+def test_solve_structures_batch_matches_single_solves():
+    """Many drop-in Structures of one topology in one launch == solving them one by one."""
+    from beamfe2_b200 import Solver, sweep
+    P = sweep.p20_draw_params(6)
+    many, single = [], []
+    for row in P:
+        for lst in (many, single):
+            s = build(sweep.p20_model_dict(row))
+            apply(s, sweep.p20_model_dict(row)['load_cases'][2])
+            lst.append(s)
+    flags = Solver.solve_structures(many)
+    assert flags == [(True, True)] * 6
+    for a, b in zip(many, single):
+        assert b.solver['linear static'].solve() and b.solver['modal'].solve()
+        assert np.array_equal(a.results['linear static'].displacement_results[0], b.results['linear static'].displacement_results[0])
+        assert np.array_equal(a.results['linear static'].reaction_forces_asvector, b.results['linear static'].reaction_forces_asvector)
+        assert a.results['modal'].circular_frequencies == b.results['modal'].circular_frequencies
+        assert np.array_equal(a.results['modal'].modeshape(3), b.results['modal'].modeshape(3))
+    other = build(util.golden_models()['chopra_102'])
+    with pytest.raises(ValueError):
+        Solver.solve_structures([many[0], other])
