@@ -527,8 +527,9 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
     std::sort(p->fixed.begin(), p->fixed.end());                       // Structure.py:180
     for (int k = 0; k < n_fixed; ++k) {
         if (p->fixed[k] < 0 || p->fixed[k] >= p->sumdof || (k > 0 && p->fixed[k] == p->fixed[k - 1])) {
+            const int bad = p->fixed[k];
             delete p;
-            return fail(-1, "fixed position %d out of range or duplicated", p->fixed[k]);
+            return fail(-1, "fixed position %d out of range or duplicated", bad);
         }
     }
     p->free_of_pos.assign(p->sumdof, 0);
