@@ -102,8 +102,31 @@ def rh_beam_load_types():
     return orc.BEAM_LOAD_KINDS
 
 
+def test_helpers_transfer_matrix():
+    from beamfe2_b200 import helpers
+    from oracle import beamfe2_oracle as orc
+    for al in (0.0, 0.3, -2.1, math.atan(0.5)):
+        assert np.allclose(helpers.transfer_matrix(al), orc.transfer_matrix(al), atol=0)
+        assert np.allclose(helpers.transfer_matrix(al, blocks=1), orc.rotation3(al), atol=0)
+        assert np.allclose(helpers.transfer_matrix(math.degrees(al), asdegree=True), orc.transfer_matrix(al), atol=1e-15)
+    assert helpers.transfer_matrix(0.1, blocks=1, blocksize=2).shape == (2, 2)
+    assert helpers.np_matrix_tolist(np.matrix([[1, 2], [3, 4]])) == [1, 2, 3, 4]
+
+
 # ------------------------------------------------------------------------------------ GPU
 gpu = pytest.mark.gpu
+
+
+@gpu
+def test_helpers_compile_global_matrix():
+    from beamfe2_b200 import helpers
+    for case in ('allresults_2', 'chopra_105'):
+        g = util.golden(case)
+        s = build(util.golden_models()[case])
+        K = helpers.compile_global_matrix(s.beams, stiffness=True)
+        M = helpers.compile_global_matrix(s.beams, mass=True)
+        assert util.relmax(np.tril(K), np.tril(g['K'])) < 1e-14
+        assert util.relmax(np.tril(M), np.tril(g['M'])) < 1e-14
 
 
 @gpu
