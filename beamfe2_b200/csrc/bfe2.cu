@@ -341,6 +341,64 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
     }
 }
 
+// ---- K3 (unfused static solve), throughput variant: WARP PER STRUCTURE, persistent blocks, integer plan cached
+//      in shared memory, warp-cooperative band Cholesky (fewer warp instructions than the one-thread version the
+//      fused kernel uses for latency), substitutions one lane per load case, everything else lane-strided.
+constexpr int K3_WARPS = 8;
+
+__global__ void __launch_bounds__(K3_WARPS * 32)
+k_static_warp(PlanDev P, BatchArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int n = P.n, C = A.C;
+    const int per_warp = ((2 * P.nN + 4 * P.nE + 3 * P.nE + P.nslots + n + C * (n + 3 * P.nN + 6 * P.nE)) + 1) & ~1;
+    // block-shared plan cache
+    int* c_conn = reinterpret_cast<int*>(smem + (size_t)nw * per_warp);
+    int* c_fop = c_conn + 2 * P.nE;
+    int* c_pof = c_fop + P.sumdof;
+    int* c_nptr = c_pof + n;
+    int* c_ninc = c_nptr + P.nN + 1;
+    for (int i = tid; i < 2 * P.nE; i += blockDim.x) { c_conn[i] = P.conn[i]; c_ninc[i] = P.node_inc[i]; }
+    for (int i = tid; i < P.sumdof; i += blockDim.x) c_fop[i] = P.free_of_pos[i];
+    for (int i = tid; i < n; i += blockDim.x) c_pof[i] = P.pos_of_free[i];
+    for (int i = tid; i <= P.nN; i += blockDim.x) c_nptr[i] = P.node_ptr[i];
+    __syncthreads();
+    PlanDev Q = P;
+    Q.conn = c_conn; Q.free_of_pos = c_fop; Q.pos_of_free = c_pof; Q.node_ptr = c_nptr; Q.node_inc = c_ninc;
+    double* w_coords = smem + (size_t)warp * per_warp;
+    double* w_props = w_coords + 2 * P.nN;
+    double* w_geo = w_props + 4 * P.nE;
+    double* w_Kb = w_geo + 3 * P.nE;
+    double* w_inv = w_Kb + P.nslots;
+    double* w_f = w_inv + n;
+    double* w_ufull = w_f + C * n;
+    double* w_ef = w_ufull + C * P.sumdof;
+    const long long nwarps = (long long)gridDim.x * nw;
+    for (long long b = (long long)blockIdx.x * nw + warp; b < A.B; b += nwarps) {
+        for (int i = lane; i < 2 * P.nN; i += 32) w_coords[i] = A.coords[b * 2 * P.nN + i];
+        for (int i = lane; i < 4 * P.nE; i += 32) w_props[i] = A.props[b * 4 * P.nE + i];
+        for (int i = lane; i < P.nslots; i += 32) w_Kb[i] = A.Kb_in[b * P.nslots + i];
+        __syncwarp();
+        stage_geometry(Q, w_coords, w_geo, lane, 32);
+        const int info = band_cholesky_warp(w_Kb, w_inv, n, P.hbw, lane);
+        __syncwarp();
+        if (info != 0) {
+            if (lane == 0) A.info[b] = info;
+            fill_nan(A.u + b * C * P.sumdof, (long long)C * P.sumdof, lane, 32);
+            fill_nan(A.endforces ? A.endforces + b * C * P.nE * 6 : nullptr, (long long)C * P.nE * 6, lane, 32);
+            fill_nan(A.reactions ? A.reactions + b * C * P.sumdof : nullptr, (long long)C * P.sumdof, lane, 32);
+            __syncwarp();
+            continue;
+        }
+        stage_static<true>(Q, C, w_props, w_geo, w_Kb, w_inv, w_f, w_ufull, w_ef, A.f_nodal + b * C * P.sumdof,
+                           A.r_local ? A.r_local + b * C * P.nE * 6 : nullptr, A.u + b * C * P.sumdof,
+                           A.endforces ? A.endforces + b * C * P.nE * 6 : nullptr,
+                           A.reactions ? A.reactions + b * C * P.sumdof : nullptr, lane, 32);
+        if (lane == 0) A.info[b] = 0;
+        __syncwarp();
+    }
+}
+
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
 //   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
 //   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
@@ -698,16 +756,21 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     A.B = B; A.C = C; A.do_static = 1; A.do_modal = 0; A.max_sweeps = BFE2_MAX_SWEEPS;
     A.coords = coords; A.props = props; A.f_nodal = f_nodal; A.r_local = r_local; A.Kb_in = Kb;
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.info = info;
-    // the static-only kernel does not need the Jacobi lanes: smallest instantiation, no W region
-    PlanDev P = plan->dev;
-    P.npad = 0; P.LD = 0;
-    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
-    const size_t bytes = (size_t)L.total * sizeof(double);
+    const size_t per_warp = (size_t)(((2 * plan->nN + 4 * plan->nE + 3 * plan->nE + plan->nslots + plan->n +
+                                       C * (plan->n + 3 * plan->nN + 6 * plan->nE)) + 1) & ~1) * sizeof(double);
+    const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1) * sizeof(int) + 16;
+    int nw = K3_WARPS;
+    while (nw > 1 && nw * per_warp + cache > 110 * 1024) --nw;
+    const size_t bytes = nw * per_warp + cache;
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
-    auto kern = k_solve<5, 2, 64, 8, false, false>;
-    BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
-    kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
+    BFE2_CUDA(cudaFuncSetAttribute(k_static_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int dev = 0, sms = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
+    const long long want = (B + nw - 1) / nw;
+    const int grid = (int)std::min<long long>(want, (long long)sms * resident);
+    k_static_warp<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(plan->dev, A);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }

@@ -379,6 +379,13 @@ __device__ __forceinline__ void band_backsolve_thread(const double* Lb, const do
 //   u = K^-1 f on the free DOFs, 0 at supports      (Solver.py:76-87 with condensation)
 //   endforces = Ke u_local - r_local                (Results.py:48-79, HermitianBeam_2D.py:336-351)
 //   reactions = sum_e R(alpha_e) endforces - f_nodal (Results.py:92-127)
+template <bool WARP_SCOPE>
+__device__ __forceinline__ void scope_sync() {
+    if (WARP_SCOPE) __syncwarp();
+    else __syncthreads();
+}
+
+template <bool WARP_SCOPE = false>
 __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const double* s_props, const double* s_geo,
                                              const double* s_Kb, const double* s_invK,
                                              double* s_f, double* s_ufull, double* s_ef,
@@ -404,14 +411,14 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
         }
         s_f[c * n + j] = v;
     }
-    __syncthreads();
+    scope_sync<WARP_SCOPE>();
     // 2. one thread per load case: L L^T u = f
     for (int c = tid; c < C; c += nt) {
         if (P.hbw <= 5) band_subst_thread<5, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
         else if (P.hbw <= 8) band_subst_thread<8, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
         else band_solve_thread(s_Kb, s_invK, s_f + c * n, n, P.hbw);
     }
-    __syncthreads();
+    scope_sync<WARP_SCOPE>();
     // 3. expand to all DOFs (exact zeros at supports), write u
     for (int t = tid; t < C * sumdof; t += nt) {
         const int c = t / sumdof, pos = t % sumdof;
@@ -420,7 +427,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
         s_ufull[t] = v;
         g_u[t] = v;
     }
-    __syncthreads();
+    scope_sync<WARP_SCOPE>();
     if (g_ef == nullptr && g_react == nullptr) return;
     // 4. local end forces per (load case, beam)
     for (int t = tid; t < C * nE; t += nt) {
@@ -456,7 +463,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
         }
     }
     if (g_react == nullptr) return;
-    __syncthreads();
+    scope_sync<WARP_SCOPE>();
     // 5. global reactions per (load case, position)
     for (int t = tid; t < C * sumdof; t += nt) {
         const int c = t / sumdof, pos = t % sumdof;

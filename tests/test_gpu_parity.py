@@ -153,9 +153,12 @@ def test_static_unfused_equals_fused_and_oracle():
     Kb, _ = batch.assemble_banded(plan, pk['coords'], pk['props'], None, want_mass=False)
     s = batch.static_solve(plan, Kb, pk['coords'], pk['props'], pk['f_nodal'], pk['r_local'])
     f = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], modal=False)
-    for k in ('u', 'endforces', 'reactions', 'info'):
-        assert torch.equal(s[k], f[k]), k
-    assert (s['info'] == 0).all()
+    # K3 is the warp-per-structure throughput kernel (warp-cooperative Cholesky), the fused kernel factorises in one
+    # thread with rsqrt seeds: same algorithm, different rounding in the last bits
+    assert torch.equal(s['info'], f['info']) and (s['info'] == 0).all()
+    for k in ('u', 'endforces', 'reactions'):
+        a, b = s[k].cpu().numpy(), f[k].cpu().numpy()
+        assert (np.abs(a - b).max(axis=tuple(range(1, a.ndim))) / np.abs(b).max(axis=tuple(range(1, a.ndim)))).max() < 1e-10, k
     o = oracle_p20(pk)
     u = s['u'].cpu().numpy()
     for b in range(300):
