@@ -374,3 +374,29 @@ def test_degenerate_eigenvalues_subspace():
         Pr_g = Pg[k:k + 2].T @ Pg[k:k + 2] @ M
         Pr_s = Ps[k:k + 2].T @ Ps[k:k + 2] @ M
         assert np.abs(Pr_g - Pr_s).max() < 1e-8
+
+
+def test_maximum_size_of_the_jacobi_path():
+    """n_free = 116 is the largest generalized eigenproblem the shared-memory Jacobi accepts; 117 is refused loudly
+    (the static path has no such limit)."""
+    nE = 39
+    xy = np.stack([np.arange(nE + 1) * 50.0, np.zeros(nE + 1)], axis=1)
+    conn = np.stack([np.arange(nE), np.arange(1, nE + 1)], axis=1).astype(np.int32)
+    props = np.tile(np.array([2.1e5, 30.0, 22.5, 7.85e-9]), (nE, 1))
+    f = np.zeros((1, 1, 3 * (nE + 1)))
+    f[0, 0, -2] = -10.0
+    for fixed, ok in (([0, 1, 2, 3 * nE + 1], True), ([0, 1, 2], False)):
+        plan = Plan(nE + 1, conn, fixed)
+        assert plan.n_free == (116 if ok else 117)
+        if ok:
+            out = batch.solve_fused(plan, T(xy[None]), T(props[None]), None, T(f), None, n_modes=5)
+            assert int(out['info'][0]) == 0
+            o = orc.solve_batch(conn, fixed, xy, props, np.zeros((nE + 1, 2)), f[0], None)
+            lam = out['lam'][0].cpu().numpy()
+            assert (np.abs(lam / o['lam'] - 1) < 1e-10 + 64 * EPS * o['lam'][-1] / o['lam']).all()
+            assert util.relmax(out['u'][0].cpu().numpy(), o['u']) < 1e-9
+        else:
+            with pytest.raises(Exception, match='Jacobi'):
+                batch.solve_fused(plan, T(xy[None]), T(props[None]), None, T(f), None, n_modes=5)
+            st = batch.solve_fused(plan, T(xy[None]), T(props[None]), None, T(f), None, modal=False)
+            assert int(st['info'][0]) == 0
