@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Soak run: many shards of the P20 sweep through the fused kernel; cheap invariants on every structure and an
+oracle comparison (numpy.linalg.solve / scipy.linalg.eigh with LAPACK's error bound) on a random subset."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from beamfe2_b200 import batch, sweep            # noqa: E402
+from beamfe2_b200.plan import Plan                # noqa: E402
+from oracle import beamfe2_oracle as orc          # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--shards', type=int, default=16)
+ap.add_argument('--batch', type=int, default=100000)
+ap.add_argument('--check', type=int, default=32)
+args = ap.parse_args()
+dev = 'cuda:0'
+conn, sup = sweep.p20_topology()
+plan = Plan.from_supports(21, conn, sup)
+fixed = orc.positions_to_eliminate(sup)
+free = torch.as_tensor(plan.pos_of_free.astype(np.int64), device=dev)
+eps = np.finfo(float).eps
+worst = dict(u=0.0, lam=0.0, sweeps=0, eq=0.0)
+for shard in range(100, 100 + args.shards):
+    P = sweep.p20_draw_params(args.batch, shard=shard)
+    pk = sweep.p20_pack(torch.from_numpy(P).to(dev))
+    out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'], n_modes=10)
+    assert bool((out['info'] == 0).all()), 'info != 0 in shard %d' % shard
+    lam = out['lam']
+    assert bool((lam[:, 1:] >= lam[:, :-1]).all()) and bool((lam > 0).all())
+    react = out['reactions']
+    eq = float((react[:, :, free].abs().amax(dim=(1, 2)) / react.abs().amax(dim=(1, 2))).max())
+    worst['eq'] = max(worst['eq'], eq)
+    worst['sweeps'] = max(worst['sweeps'], int(out['sweeps'].max()))
+    idx = np.random.default_rng(shard).choice(args.batch, args.check, replace=False)
+    h = {k: v[idx].cpu().numpy() for k, v in pk.items()}
+    o = orc.solve_batch(conn, fixed, h['coords'], h['props'], h['nodal_mass'], h['f_nodal'], h['r_local'], n_modes=10)
+    u = out['u'][idx].cpu().numpy()
+    eu = (np.abs(u - o['u']).max(axis=(1, 2)) / np.abs(o['u']).max(axis=(1, 2))).max()
+    lm = lam[idx].cpu().numpy()
+    el = (np.abs(lm / o['lam'] - 1) / (1e-10 + 64 * eps * o['lam'][:, -1:] / o['lam'])).max()
+    worst['u'] = max(worst['u'], float(eu))
+    worst['lam'] = max(worst['lam'], float(el))
+    assert eu < 1e-10 and el < 1.0, (shard, eu, el)
+print('soak ok: %d structures, worst %s' % (args.shards * args.batch, worst))
