@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -59,7 +60,9 @@ struct bfe2_plan {
     int npad = 0, LD = 0, rpl = 0, lpp = 0, nthreads = 0;
     std::vector<int32_t> conn, free_of_pos, pos_of_free, fixed, slot_ptr, contrib, node_ptr, node_inc;
     std::vector<uint8_t> lumped;
-    // device mirror (uploaded lazily on the first launch, on the then-current device)
+    // device mirror: uploaded lazily on the first launch on a device; one copy per device is kept (a plan may be
+    // used from several devices, e.g. one thread per GPU), `dev` always describes the CURRENT device's copy
+    std::map<int, std::pair<void*, PlanDev>> copies;
     bool uploaded = false;
     int device = -1;
     void* d_blob = nullptr;
@@ -133,7 +136,16 @@ int plan_upload(bfe2_plan* p) {
     int dev = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
     if (p->uploaded && p->device == dev) return 0;
-    if (p->uploaded) { cudaFree(p->d_blob); p->uploaded = false; p->d_blob = nullptr; }
+    {
+        auto it = p->copies.find(dev);
+        if (it != p->copies.end()) {                  // already resident on this device: switch to that copy
+            p->d_blob = it->second.first;
+            p->dev = it->second.second;
+            p->device = dev;
+            p->uploaded = true;
+            return 0;
+        }
+    }
     // one blob: all int32 arrays then the uint8 flags
     const std::vector<int32_t>* arrs[7] = {&p->conn, &p->free_of_pos, &p->pos_of_free, &p->slot_ptr,
                                            &p->contrib, &p->node_ptr, &p->node_inc};
@@ -162,6 +174,7 @@ int plan_upload(bfe2_plan* p) {
     d.lumped = reinterpret_cast<const uint8_t*>(base + off[7]);
     p->uploaded = true;
     p->device = dev;
+    p->copies[dev] = std::make_pair(p->d_blob, p->dev);
     return 0;
 }
 
@@ -660,7 +673,12 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
 
 void bfe2_plan_destroy(bfe2_plan* plan) {
     if (!plan) return;
-    if (plan->uploaded && plan->d_blob) cudaFree(plan->d_blob);
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (auto& kv : plan->copies) {
+        if (cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second.first);
+    }
+    if (have_cur) cudaSetDevice(cur);
     delete plan;
 }
 

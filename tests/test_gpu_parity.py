@@ -400,3 +400,22 @@ def test_maximum_size_of_the_jacobi_path():
                 batch.solve_fused(plan, T(xy[None]), T(props[None]), None, T(f), None, n_modes=5)
             st = batch.solve_fused(plan, T(xy[None]), T(props[None]), None, T(f), None, modal=False)
             assert int(st['info'][0]) == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_one_plan_on_two_devices():
+    """A plan keeps one device copy per GPU: alternating devices must neither re-upload nor free a copy in use."""
+    conn, sup = sweep.p20_topology()
+    plan = Plan.from_supports(21, conn, sup)
+    P = sweep.p20_draw_params(64)
+    outs = []
+    for rep in range(3):
+        for d in (0, 1):
+            pk = sweep.p20_pack(torch.from_numpy(P).to('cuda:%d' % d))
+            outs.append(batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'],
+                                          pk['r_local'], n_modes=4))
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    ref = outs[0]
+    for o in outs[1:]:
+        assert torch.equal(o['lam'].cpu(), ref['lam'].cpu()) and torch.equal(o['u'].cpu(), ref['u'].cpu())
