@@ -412,6 +412,344 @@ k_static_warp(PlanDev P, BatchArgs A) {
     }
 }
 
+// ---- K3 (narrow bands) and the static-only fused path: G lanes per structure -----------------------
+//   A warp carries 32/G structures at once.  The stages whose work items are independent (beam
+//   coefficients, band slots, right-hand sides, end forces, reactions, loads / stores) are spread over
+//   the G lanes of the group; the two sequential stages run on lane 0 (register-window band Cholesky)
+//   and lanes 0..C-1 (one substitution per load case) of EVERY group of the warp at the same time, so a
+//   warp instruction of those stages serves 32/G structures instead of one.  No block barrier after the
+//   plan cache is filled: groups only need __syncwarp.
+//
+//   Beam stiffness in global axes in closed form (the seven distinct numbers of T k T^T,
+//   HermitianBeam_2D.py:173-175 / :284-297):
+//     p = a c^2 + b12 s^2, q = (a - b12) c s, r = a s^2 + b12 c^2, t = b6 s, w = b6 c, b4, b2
+//   c_ke7[6 r + c] = +-(1 + index into {p,q,r,t,w,b4,b2}).
+__constant__ signed char c_ke7[36] = {+1, +2, -4, -1, -2, -4,
+                                      +2, +3, +5, -2, -3, +5,
+                                      -4, +5, +6, +4, -5, +7,
+                                      -1, -2, +4, +1, +2, +4,
+                                      -2, -3, -5, +2, +3, -5,
+                                      -4, +5, +7, +4, -5, +6};
+
+struct GroupLayout { int a, kb, per_group; };
+
+__host__ __device__ inline GroupLayout group_layout(int nE, int n, int nslots, int C, int G) {
+    GroupLayout L;
+    const int size_a = (8 * nE > C * n) ? 8 * nE : C * n;           // beam stiffness numbers | right-hand sides
+    L.a = 5 * nE;                                 // after geo[nE][5] = 1/L, cos, sin, EA/L, EI/L
+    L.kb = L.a + size_a;                          // band [nslots] + 1/diag [n] | end forces [C][nE][6]
+    int tot = L.kb + ((nslots + n > 6 * C * nE) ? nslots + n : 6 * C * nE);
+    // group stride = G (mod 16 doubles): the groups of a half-warp tile the banks in the lane-parallel stages;
+    // G >= 16: stride = 2 (mod 16) keeps lane 0 of the warp's groups apart in the lane-serial stages
+    const int want = G < 16 ? G : 2;
+    tot += ((want - tot) % 16 + 16) % 16;
+    L.per_group = tot;
+    return L;
+}
+
+// 8-byte asynchronous global -> shared copies (LDGSTS): the unfused path puts the whole band of a structure in
+// flight at once and it lands while the group works out the beam geometry.
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G, int HB, bool ASSEMBLE>
+__global__ void __launch_bounds__(640)
+k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, g = tid % G, gi = tid / G, ngb = blockDim.x / G;
+    const int n = P.n, nE = P.nE, nN = P.nN, sumdof = P.sumdof, C = A.C, hbw = P.hbw, nslots = P.nslots;
+    const GroupLayout GL = group_layout(nE, n, nslots, C, G);
+    // block-shared plan cache (contributions already decoded to beam*8 + value index, sign in bit 31)
+    int* c_conn = reinterpret_cast<int*>(smem + (size_t)ngb * GL.per_group);
+    int* c_fop = c_conn + 2 * nE;
+    int* c_pof = c_fop + sumdof;
+    int* c_nptr = c_pof + n;
+    int* c_ninc = c_nptr + nN + 1;
+    int* c_sptr = c_ninc + 2 * nE;
+    int* c_con = c_sptr + nslots + 1;
+    for (int i = tid; i < 2 * nE; i += blockDim.x) { c_conn[i] = P.conn[i]; c_ninc[i] = P.node_inc[i]; }
+    for (int i = tid; i < sumdof; i += blockDim.x) c_fop[i] = P.free_of_pos[i];
+    for (int i = tid; i < n; i += blockDim.x) c_pof[i] = P.pos_of_free[i];
+    for (int i = tid; i <= nN; i += blockDim.x) c_nptr[i] = P.node_ptr[i];
+    if (ASSEMBLE) {
+        for (int i = tid; i <= nslots; i += blockDim.x) c_sptr[i] = P.slot_ptr[i];
+        for (int i = tid; i < ncontrib; i += blockDim.x) {
+            const int idx = P.contrib[i];
+            const int code = c_ke7[idx % 36];
+            c_con[i] = ((idx / 36) * 8 + (code < 0 ? -code : code) - 1) | (code < 0 ? (int)0x80000000 : 0);
+        }
+    }
+    __syncthreads();
+    double* s_geo = smem + (size_t)gi * GL.per_group;            // [nE][5] = 1/L, cos, sin, EA/L, EI/L
+    double* s_a = s_geo + GL.a;                                   // beam stiffness numbers, then right-hand sides
+    double* s_Kb = s_geo + GL.kb;
+    double* s_inv = s_Kb + nslots;
+    double* s_ef = s_Kb;                                          // the band is dead once u is known
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const long long per_pass = (long long)gridDim.x * ngb;
+    const long long passes = (A.B + per_pass - 1) / per_pass;
+    const int nr = 6 * C * nE, nf = C * sumdof;
+    const bool have_r = A.r_local != nullptr;
+    auto structure_of = [&](long long it) {
+        const long long b0 = (it * gridDim.x + blockIdx.x) * ngb + gi;
+        return b0 < A.B ? b0 : A.B - 1;                           // idle groups redo the last structure, no stores
+    };
+    for (long long it = 0; it < passes; ++it) {
+        const bool valid = (it * gridDim.x + blockIdx.x) * ngb + gi < A.B;
+        const long long b = structure_of(it);
+        const double* g_f = A.f_nodal + b * (long long)nf;
+        const double* g_r = have_r ? A.r_local + b * (long long)nr : nullptr;
+        const double* p_cp = A.coords + b * 2 * nN;
+        const double* p_pr = A.props + b * 4 * nE;
+        if (!ASSEMBLE) {                                          // unfused K3: the band comes from HBM
+            const double* g_Kb = A.Kb_in + b * nslots;
+            for (int slot = g; slot < nslots; slot += G) cp_async8(s_Kb + slot, g_Kb + slot);
+            cp_async_commit();
+        }
+        // 0. (fused path) this lane's right-hand-side entries go into registers and r_local into the band region,
+        //    which is free until the assembly: every load of the right-hand sides is in flight before the first
+        //    use, instead of one dependent HBM round trip per incident beam.  Item k of a lane is the flat index
+        //    t = g + G k = c n + j.
+        constexpr int MAXI = 12;
+        const bool early_rhs = ASSEMBLE && have_r && (C * n + G - 1) / G <= MAXI && nr <= nslots + n;
+        double xr[MAXI];
+        if (early_rhs) {
+            for (int i = g; i < nr; i += G) cp_async8(s_Kb + i, g_r + i);
+            cp_async_commit();
+            int c = 0, j = g;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k) {
+                while (j >= n) { j -= n; ++c; }
+                xr[k] = (c < C) ? g_f[c * sumdof + c_pof[j]] : 0.0;
+                j += G;
+            }
+        }
+        // 1. beams: direction, 1/L, EA/L, EI/L and (fused path) the seven stiffness numbers
+        for (int e = g; e < nE; e += G) {
+            const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
+            const double dx = p_cp[2 * nj] - p_cp[2 * ni], dy = p_cp[2 * nj + 1] - p_cp[2 * ni + 1];
+            const double* pr = p_pr + 4 * e;
+            const double iL = rsqrt_fast(fma(dx, dx, dy * dy));
+            const double cs = dx * iL, sn = dy * iL;
+            const double a = (pr[0] * pr[1]) * iL, eil = (pr[0] * pr[2]) * iL;
+            double* ge = s_geo + 5 * e;
+            ge[0] = iL; ge[1] = cs; ge[2] = sn; ge[3] = a; ge[4] = eil;
+            if (ASSEMBLE) {
+                const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL;
+                double* k7 = s_a + 8 * e;
+                k7[0] = fma(a * cs, cs, (b12 * sn) * sn);
+                k7[1] = ((a - b12) * cs) * sn;
+                k7[2] = fma(a * sn, sn, (b12 * cs) * cs);
+                k7[3] = b6 * sn;
+                k7[4] = b6 * cs;
+                k7[5] = 4.0 * eil;
+                k7[6] = 2.0 * eil;
+            }
+        }
+        if (early_rhs) {
+            cp_async_wait<0>();
+            __syncwarp();
+            int c = 0, j = g;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k) {
+                while (j >= n) { j -= n; ++c; }
+                if (c < C) {
+                    const int pos = c_pof[j];
+                    const int node = pos / 3, dof = pos - 3 * node;
+                    double v = xr[k];
+                    for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
+                        const int inc = c_ninc[q];
+                        const int e = inc >> 1;
+                        const double* r = s_Kb + (c * nE + e) * 6 + 3 * (inc & 1);
+                        const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
+                        if (dof == 0) v += cs * r[0] - sn * r[1];
+                        else if (dof == 1) v += sn * r[0] + cs * r[1];
+                        else v += r[2];
+                    }
+                    xr[k] = v;
+                }
+                j += G;
+            }
+        }
+        __syncwarp();
+        // 2. band of K on the free DOFs
+        if (ASSEMBLE) {
+            for (int slot = g; slot < nslots; slot += G) {
+                double k = 0.0;
+                for (int q = c_sptr[slot]; q < c_sptr[slot + 1]; ++q) {
+                    const int code = c_con[q];
+                    const double v = s_a[code & 0x7fffffff];
+                    k += (code < 0) ? -v : v;
+                }
+                s_Kb[slot] = k;
+            }
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        // 3. factor: lane 0 of each group
+        const int info = band_cholesky_group<G, HB>(s_Kb, s_inv, n, hbw, g);
+        // 4. right-hand sides in free numbering (over the stiffness numbers, which are dead now)
+        if (early_rhs) {
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k)
+                if (g + G * k < C * n) s_a[g + G * k] = xr[k];
+        }
+        for (int c = 0; c < (early_rhs ? 0 : C); ++c) {
+            for (int j = g; j < n; j += G) {
+                const int pos = c_pof[j];
+                double v = g_f[c * sumdof + pos];
+                if (have_r) {
+                    const int node = pos / 3, k = pos - 3 * node;
+                    for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
+                        const int inc = c_ninc[q];
+                        const int e = inc >> 1;
+                        const double* r = g_r + (c * nE + e) * 6 + 3 * (inc & 1);
+                        const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
+                        if (k == 0) v += cs * r[0] - sn * r[1];
+                        else if (k == 1) v += sn * r[0] + cs * r[1];
+                        else v += r[2];
+                    }
+                }
+                s_a[c * n + j] = v;
+            }
+        }
+        __syncwarp();
+        // 5. substitute: one lane per load case
+        for (int c = g; c < C; c += G) {
+            if (hbw == HB) band_subst_exact<HB>(s_Kb, s_inv, s_a + c * n, n);
+            else band_subst_thread<HB, true, true>(s_Kb, s_inv, s_a + c * n, 1, n, hbw);
+        }
+        __syncwarp();
+        const bool ok = info == 0;
+        if (valid && g == 0) A.info[b] = info;
+        // 6. displacements on all DOFs (exact zeros at supports)
+        {
+            double* g_u = A.u + b * (long long)nf;
+            for (int c = 0; c < C; ++c)
+                for (int pos = g; pos < sumdof; pos += G) {
+                    const int j = c_fop[pos];
+                    const double v = (j >= 0) ? s_a[c * n + j] : 0.0;
+                    if (valid) g_u[c * sumdof + pos] = ok ? v : qnan;
+                }
+        }
+        if (A.endforces == nullptr && A.reactions == nullptr) { __syncwarp(); continue; }
+        // 7. local end forces  Ke u_local - r_local  (Results.py:48-79)
+        double* g_ef = A.endforces ? A.endforces + b * (long long)nr : nullptr;
+        for (int e = g; e < nE; e += G) {
+            const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
+            const double* ge = s_geo + 5 * e;
+            const double iL = ge[0], cs = ge[1], sn = ge[2], a = ge[3], eil = ge[4];
+            const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL, b4 = 4.0 * eil, b2 = 2.0 * eil;
+            const int fi0 = c_fop[3 * ni], fi1 = c_fop[3 * ni + 1], fi2 = c_fop[3 * ni + 2];
+            const int fj0 = c_fop[3 * nj], fj1 = c_fop[3 * nj + 1], fj2 = c_fop[3 * nj + 2];
+            for (int c = 0; c < C; ++c) {
+                const double* x = s_a + c * n;
+                const double ui0 = fi0 >= 0 ? x[fi0] : 0.0, ui1 = fi1 >= 0 ? x[fi1] : 0.0, ui2 = fi2 >= 0 ? x[fi2] : 0.0;
+                const double uj0 = fj0 >= 0 ? x[fj0] : 0.0, uj1 = fj1 >= 0 ? x[fj1] : 0.0, uj2 = fj2 >= 0 ? x[fj2] : 0.0;
+                const double d0 = cs * ui0 + sn * ui1, d1 = cs * ui1 - sn * ui0;
+                const double d3 = cs * uj0 + sn * uj1, d4 = cs * uj1 - sn * uj0;
+                double q[6];
+                q[0] = a * (d0 - d3);
+                q[3] = -q[0];
+                q[1] = fma(b12, d1 - d4, b6 * (ui2 + uj2));
+                q[4] = -q[1];
+                q[2] = fma(b6, d1 - d4, fma(b4, ui2, b2 * uj2));
+                q[5] = fma(b6, d1 - d4, fma(b2, ui2, b4 * uj2));
+                double* d = s_ef + (c * nE + e) * 6;
+                if (have_r) {
+                    const double* r = g_r + (c * nE + e) * 6;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) q[k] -= r[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d[k] = q[k];
+                if (g_ef != nullptr && valid) {
+                    double* o = g_ef + (c * nE + e) * 6;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) o[k] = ok ? q[k] : qnan;
+                }
+            }
+        }
+        __syncwarp();
+        // 8. reactions per (load case, position)  (Results.py:92-127)
+        if (A.reactions != nullptr) {
+            double* g_re = A.reactions + b * (long long)nf;
+            for (int c = 0; c < C; ++c)
+                for (int pos = g; pos < sumdof; pos += G) {
+                    const int node = pos / 3, k = pos - 3 * node;
+                    double v = 0.0;
+                    for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
+                        const int inc = c_ninc[q];
+                        const int e = inc >> 1;
+                        const double* f = s_ef + (c * nE + e) * 6 + 3 * (inc & 1);
+                        const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
+                        if (k == 0) v += cs * f[0] - sn * f[1];
+                        else if (k == 1) v += sn * f[0] + cs * f[1];
+                        else v += f[2];
+                    }
+                    if (valid) g_re[c * sumdof + pos] = ok ? v - g_f[c * sumdof + pos] : qnan;
+                }
+        }
+        __syncwarp();
+    }
+}
+
+template <int G, int HB, bool ASSEMBLE>
+int launch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+    const GroupLayout GL = group_layout(plan->nE, plan->n, plan->nslots, A.C, G);
+    const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1 + plan->nslots + 1 +
+                                  plan->ncontrib) * sizeof(int) + 16;
+    const size_t per_warp = (size_t)(32 / G) * GL.per_group * sizeof(double);
+    // as many warps per SM as the shared memory holds, in blocks of at most 20 warps
+    int nw = 0;
+    for (int nblk = 1; nblk <= 8 && nw == 0; ++nblk) {
+        const size_t avail = (227 * 1024) / nblk - 1024;
+        if (avail <= cache) break;
+        const int fit = (int)((avail - cache) / per_warp);
+        if (fit <= 20) nw = fit;
+    }
+    if (nw < 1) return 1;                         // does not fit: the caller falls back to block-per-structure
+    // small batches: do not leave SMs idle behind a few fat blocks
+    int dev = 0, sms = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    while (nw > 1 && (long long)(nw / 2) * (32 / G) * sms >= A.B) nw /= 2;
+    const size_t bytes = nw * per_warp + cache;
+    auto kern = k_static_group<G, HB, ASSEMBLE>;
+    BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const long long per_block = (long long)nw * (32 / G);
+    const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
+    const int grid = (int)std::min<long long>((A.B + per_block - 1) / per_block, (long long)sms * resident);
+    kern<<<grid, nw * 32, bytes, stream>>>(plan->dev, A, plan->ncontrib);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 0: launched; 1: this plan does not fit the group kernel (wide band / too much shared memory); < 0: error
+template <bool ASSEMBLE>
+int dispatch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+    static const int G = [] { const char* e = getenv("BFE2_STATIC_G"); return e ? atoi(e) : 16; }();
+    if (G == 0 || plan->hbw > 8 || plan->nE == 0) return 1;
+#define BFE2_SG(GG, HH) launch_static_group<GG, HH, ASSEMBLE>(plan, A, stream)
+    if (plan->hbw <= 5) {
+        if (G == 4) return BFE2_SG(4, 5);
+        if (G == 16) return BFE2_SG(16, 5);
+        if (G == 32) return BFE2_SG(32, 5);
+        return BFE2_SG(8, 5);
+    }
+    if (G == 4) return BFE2_SG(4, 8);
+    if (G == 16) return BFE2_SG(16, 8);
+    if (G == 32) return BFE2_SG(32, 8);
+    return BFE2_SG(8, 8);
+#undef BFE2_SG
+}
+
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
 //   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
 //   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
@@ -774,6 +1112,7 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     A.B = B; A.C = C; A.do_static = 1; A.do_modal = 0; A.max_sweeps = BFE2_MAX_SWEEPS;
     A.coords = coords; A.props = props; A.f_nodal = f_nodal; A.r_local = r_local; A.Kb_in = Kb;
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.info = info;
+    if (const int r = dispatch_static_group<false>(plan, A, (cudaStream_t)stream); r <= 0) return r;
     const size_t per_warp = (size_t)(((2 * plan->nN + 4 * plan->nE + 3 * plan->nE + plan->nslots + plan->n +
                                        C * (plan->n + 3 * plan->nN + 6 * plan->nE)) + 1) & ~1) * sizeof(double);
     const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1) * sizeof(int) + 16;
@@ -831,6 +1170,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.lam = lam; A.phi = phi;
     A.info = info; A.sweeps = sweeps;
     if (!do_modal) {
+        if (const int r = dispatch_static_group<true>(plan, A, (cudaStream_t)stream); r <= 0) return r;
         PlanDev P = plan->dev;
         P.npad = 0; P.LD = 0;
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);

@@ -348,6 +348,82 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
     }
 }
 
+// The factorisation by the G lanes of a group (the warp's groups run it in lockstep, each on its own band):
+// per column, lanes 1..m scale the subdiagonal, then lane t takes the trailing-update pair (p, q) number t.
+// In place in shared memory; 1 / L[j][j] goes to invdiag, which holds the ORIGINAL diagonal until column j is
+// eliminated (the relative pivot test).  Returns 0 or the 1-based column of the first bad pivot, uniform per
+// group; a failed group keeps running in lockstep without storing.
+template <int G, int HB>
+__device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, int n, int b, int g) {
+    for (int j = g; j < n; j += G) invdiag[j] = Ab[j];
+    constexpr int NP = HB * (HB + 1) / 2, ROUNDS = (NP + G - 1) / G;
+    int off_t[ROUNDS], off_p[ROUNDS], off_q[ROUNDS], need[ROUNDS];
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const int t = g + k * G;
+        int p = 1;
+        while (p * (p + 1) / 2 <= t) ++p;            // t = p (p - 1) / 2 + (q - 1), 1 <= q <= p
+        const int q = t - p * (p - 1) / 2 + 1;
+        need[k] = (t < NP) ? p : HB + 1;             // the pair exists in a column with m >= p
+        off_p[k] = p * n;
+        off_q[k] = q * n;
+        off_t[k] = (p - q) * n + q;
+    }
+    __syncwarp();
+    int info = 0;
+    for (int col = 0; col < n; ++col) {
+        const int m = min(b, n - 1 - col);
+        const double piv = Ab[col];
+        const double orig = invdiag[col];
+        if (info == 0 && (!(piv > 1.4210854715202004e-14 * orig) || !isfinite(piv))) info = col + 1;
+        const double r = rsqrt_fast(piv);
+        if (info == 0)
+            for (int i = g; i <= m; i += G)
+                if (i > 0) Ab[i * n + col] *= r;
+        __syncwarp();
+        if (info == 0) {
+            if (g == 0) { Ab[col] = piv * r; invdiag[col] = r; }
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k)
+                if (need[k] <= m) Ab[off_t[k] + col] = fma(-Ab[off_p[k] + col], Ab[off_q[k] + col], Ab[off_t[k] + col]);
+        }
+        __syncwarp();
+    }
+    return info;
+}
+
+// Substitutions for a band that is exactly HB wide (b == HB), one thread per right-hand side, no bounds tests:
+// the band rectangle's slots outside the matrix (row j + d >= n) are never written and hold finite numbers, and
+// they only ever multiply the zeros the window starts with.
+template <int HB>
+__device__ __forceinline__ void band_subst_exact(const double* Lb, const double* invdiag, double* x, int n) {
+    double win[HB];
+#pragma unroll
+    for (int d = 0; d < HB; ++d) win[d] = 0.0;
+    for (int j = 0; j < n; ++j) {                    // L y = f:  L[j][j-d] = Lb[d * n + j - d]
+        double acc = x[j];
+#pragma unroll
+        for (int d = HB; d >= 1; --d) acc = fma(-Lb[d * (n - 1) + j], win[d - 1], acc);
+        const double v = acc * invdiag[j];
+#pragma unroll
+        for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
+        win[0] = v;
+        x[j] = v;
+    }
+#pragma unroll
+    for (int d = 0; d < HB; ++d) win[d] = 0.0;
+    for (int j = n - 1; j >= 0; --j) {               // L^T u = y:  L[j+d][j] = Lb[d * n + j]
+        double acc = x[j];
+#pragma unroll
+        for (int d = HB; d >= 1; --d) acc = fma(-Lb[d * n + j], win[d - 1], acc);
+        const double v = acc * invdiag[j];
+#pragma unroll
+        for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
+        win[0] = v;
+        x[j] = v;
+    }
+}
+
 // Forward + back substitution with the band factor, one thread per right-hand side (in place).
 __device__ __forceinline__ void band_solve_thread(const double* Lb, const double* invdiag, double* x, int n, int b) {
     for (int j = 0; j < n; ++j) {                    // L y = f

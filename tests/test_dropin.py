@@ -286,8 +286,12 @@ def test_solve_structures_batch_matches_single_solves():
     assert flags == [(True, True)] * 6
     for a, b in zip(many, single):
         assert b.solver['linear static'].solve() and b.solver['modal'].solve()
-        assert np.array_equal(a.results['linear static'].displacement_results[0], b.results['linear static'].displacement_results[0])
-        assert np.array_equal(a.results['linear static'].reaction_forces_asvector, b.results['linear static'].reaction_forces_asvector)
+        # static: the batched call runs inside the fused static+modal kernel, the single solve in the static-only
+        # kernel (closed-form beam stiffness): same algorithm, different rounding -> the north-star tolerance
+        assert util.relmax(a.results['linear static'].displacement_results[0],
+                           b.results['linear static'].displacement_results[0]) < 1e-10
+        assert util.relmax(a.results['linear static'].reaction_forces_asvector,
+                           b.results['linear static'].reaction_forces_asvector) < 1e-10
         assert a.results['modal'].circular_frequencies == b.results['modal'].circular_frequencies
         assert np.array_equal(a.results['modal'].modeshape(3), b.results['modal'].modeshape(3))
     other = build(util.golden_models()['chopra_102'])
