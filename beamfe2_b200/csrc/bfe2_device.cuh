@@ -574,6 +574,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
 //   a zero dummy column.  LPP lanes share a pair (each holds RPL rows of both columns in registers).
 // ------------------------------------------------------------------------------------------------
 #define BFE2_JACOBI_TOL 1.0e-15
+#define BFE2_JACOBI_TAU 2.5e-9             // 2 * 116 * tau^2 < tol
 
 template <int RPL, int LPP>
 __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
@@ -673,9 +674,16 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 // the next pairing has been stored to shared memory (pg_mine).
 template <int RPL, bool ODD>
 __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
-                                                 int& rotated, double g, unsigned pg_mine, bool act, bool last, int src) {
+                                                 int& unsettled, double g, unsigned pg_mine, bool act, bool last, int src) {
     // rotate when |g| > tol * sqrt(nA nB)  <=>  g^2 > tol^2 nA nB
-    const bool rot = act && !(ODD && last) && (g * g > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * (nA * nB));
+    const double gg = g * g, pab = nA * nB;
+    const bool live = act && !(ODD && last);
+    const bool rot = live && (gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab);
+    // A sweep whose cosines all start below tau and whose rotations all have |sin| below sigma leaves cosines
+    // below tol + 2 n tau sigma (each later rotation of a column moves a settled cosine by at most |sin| * cos):
+    // with 2 n tau sigma < tol it is the last one, no empty checking sweep needed (the quadratic-convergence
+    // exit of LAPACK's dgesvj, stated on both quantities).
+    if (live && gg > (BFE2_JACOBI_TAU * BFE2_JACOBI_TAU) * pab) unsettled = 1;
     double c = 1.0, s = 0.0;
     if (ODD && last && act) {                         // exchange the two idle end columns (the sign flip is
         c = 0.0; s = -1.0;                            // immaterial: columns are defined up to sign)
@@ -695,7 +703,7 @@ __device__ __forceinline__ void jacobi_regs_step(double (&A)[RPL], double (&B)[R
         const double tg = (s * ic) * g;               // t g
         nA -= tg;
         nB += tg;
-        rotated = 1;
+        if (fabs(s) > BFE2_JACOBI_TAU) unsettled = 1;
     }
     constexpr int NACC = 2;      // accumulators of the fused dot product (measured: 2 > 4 > 8, register pressure)
     double acc[NACC];
@@ -775,21 +783,21 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
                 g += part_n[(w * 32 + lane) * 3 + 2];
             }
         }
-        int rotated = 0;
+        int unsettled = 0;
 #pragma unroll 1
         for (int step = 0; step < npad; step += 2) {
-            jacobi_regs_step<RPL, false>(A, B, nA, nB, rotated, g, pg1 + mine, act, last, src_dn);
+            jacobi_regs_step<RPL, false>(A, B, nA, nB, unsettled, g, pg1 + mine, act, last, src_dn);
             __syncthreads();
             g = lds_f64(pg1 + w0);
 #pragma unroll
             for (int w = 1; w < NW; ++w) g += lds_f64(pg1 + w0 + 256u * w);
-            jacobi_regs_step<RPL, true>(A, B, nA, nB, rotated, g, pg0 + mine, act, last, src_up);
+            jacobi_regs_step<RPL, true>(A, B, nA, nB, unsettled, g, pg0 + mine, act, last, src_up);
             __syncthreads();
             g = lds_f64(pg0 + w0);
 #pragma unroll
             for (int w = 1; w < NW; ++w) g += lds_f64(pg0 + w0 + 256u * w);
         }
-        if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
+        if (!__syncthreads_or(unsettled)) { ++sweeps; converged = true; break; }
     }
     __syncthreads();                                  // scratch no longer read: W comes back
     if (act) {
