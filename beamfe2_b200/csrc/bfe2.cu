@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -788,27 +789,28 @@ k_solve(PlanDev P, BatchArgs A) {
     } else if (A.do_static) {
         stage_geometry(P, smem + L.coords, smem + L.geo, tid, nt);
     }
-    // band Cholesky: warp 0 -> K, warp 1 -> M (concurrently)
-    if (P.hbw <= 8) {                                // narrow band: one thread per matrix, window in registers
-        if (tid == 0) {
-            s_flag[0] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Kb, smem + L.invK, n, P.hbw)
-                                   : band_cholesky_thread<8>(smem + L.Kb, smem + L.invK, n, P.hbw);
-        } else if (tid == 32 && A.do_modal) {
-            s_flag[1] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Mb, smem + L.invM, n, P.hbw)
-                                   : band_cholesky_thread<8>(smem + L.Mb, smem + L.invM, n, P.hbw);
+    // band Cholesky of K (warp 0) and of M (warp 1); narrow bands: one thread per matrix, window in registers
+    auto factor = [&](bool do_k, bool do_m) {
+        if (P.hbw <= 8) {
+            if (tid == 0 && do_k) {
+                s_flag[0] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Kb, smem + L.invK, n, P.hbw)
+                                       : band_cholesky_thread<8>(smem + L.Kb, smem + L.invK, n, P.hbw);
+            } else if (tid == 32 && do_m) {
+                s_flag[1] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Mb, smem + L.invM, n, P.hbw)
+                                       : band_cholesky_thread<8>(smem + L.Mb, smem + L.invM, n, P.hbw);
+            }
+        } else if (warp == 0 && do_k) {
+            const int r = band_cholesky_warp(smem + L.Kb, smem + L.invK, n, P.hbw, lane);
+            if (lane == 0) s_flag[0] = r;
+        } else if (warp == 1 && do_m) {
+            const int r = band_cholesky_warp(smem + L.Mb, smem + L.invM, n, P.hbw, lane);
+            if (lane == 0) s_flag[1] = r;
         }
-    } else if (warp == 0) {
-        const int r = band_cholesky_warp(smem + L.Kb, smem + L.invK, n, P.hbw, lane);
-        if (lane == 0) s_flag[0] = r;
-    } else if (warp == 1 && A.do_modal) {
-        const int r = band_cholesky_warp(smem + L.Mb, smem + L.invM, n, P.hbw, lane);
-        if (lane == 0) s_flag[1] = r;
-    }
-    __syncthreads();
-    const int infoK = s_flag[0], infoM = s_flag[1];
-    if (infoK != 0 || infoM != 0) {                  // numerical failure: NaN outputs, per-structure info
+        __syncthreads();
+    };
+    auto fail_all = [&](int code) {                  // numerical failure: NaN outputs, per-structure info
         if (tid == 0) {
-            A.info[b] = infoK != 0 ? infoK : -1;
+            A.info[b] = code;
             if (A.sweeps) A.sweeps[b] = 0;
         }
         if (A.do_static) {
@@ -820,10 +822,8 @@ k_solve(PlanDev P, BatchArgs A) {
             fill_nan(A.lam + b * n, n, tid, nt);
             fill_nan(A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, (long long)A.n_modes * P.sumdof, tid, nt);
         }
-        return;
-    }
-    int info = 0;
-    if (A.do_static) {
+    };
+    auto static_stage = [&]() {
         double* s_f = smem + L.U;
         double* s_ufull = s_f + A.C * n;
         double* s_ef = s_ufull + A.C * P.sumdof;
@@ -833,20 +833,58 @@ k_solve(PlanDev P, BatchArgs A) {
                      A.u + b * A.C * P.sumdof,
                      A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr,
                      A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt);
-        __syncthreads();
-    }
-    if (A.do_modal) {
-        double* s_W = smem + L.U;
-        stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
-        int sw;
-        if constexpr (REGS) sw = stage_jacobi_regs<RPL, LPP>(P, s_W, A.max_sweeps, tid);
-        else sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
+    };
+    int info = 0;
+    if constexpr (REGS) {
+        // Modal part first, while the band of K is still unfactored:  C = Lm^-1 K Lm^-T, pivoted Cholesky
+        // C = Z Z^T and one-sided Jacobi on Z in registers; shapes phi = Lm^-T u.  Then K = Lk Lk^T for the
+        // static part (and for the "K is not positive definite" diagnosis, which wins over the modal codes).
+        int sw = 0;
+        if (A.do_modal) {
+            factor(false, true);
+            if (s_flag[1] == 0) {
+                double* s_W = smem + L.U;
+                stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
+                sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
+                if (sw != INT_MIN) {
+                    stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
+                                            A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr,
+                                            tid, nt, true);
+                }
+                __syncthreads();
+            }
+        }
+        factor(true, false);
+        const int infoK = s_flag[0], infoM = s_flag[1];
+        if (infoK != 0 || infoM != 0 || sw == INT_MIN) {
+            fail_all(infoK != 0 ? infoK : (infoM != 0 ? -1 : -2));
+            return;
+        }
         if (sw < 0) info = -2;
         if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
-        stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,
-                                A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, tid, nt);
-    } else if (tid == 0 && A.sweeps) {
-        A.sweeps[b] = 0;
+        if (A.do_static) static_stage();
+    } else {
+        factor(true, A.do_modal != 0);
+        const int infoK = s_flag[0], infoM = s_flag[1];
+        if (infoK != 0 || infoM != 0) {
+            fail_all(infoK != 0 ? infoK : -1);
+            return;
+        }
+        if (A.do_static) {
+            static_stage();
+            __syncthreads();
+        }
+        if (A.do_modal) {
+            double* s_W = smem + L.U;
+            stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
+            const int sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
+            if (sw < 0) info = -2;
+            if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
+            stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,
+                                    A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, tid, nt);
+        } else if (tid == 0 && A.sweeps) {
+            A.sweeps[b] = 0;
+        }
     }
     if (tid == 0) A.info[b] = info;
 }
