@@ -840,11 +840,25 @@ k_solve(PlanDev P, BatchArgs A) {
         // C = Z Z^T and one-sided Jacobi on Z in registers; shapes phi = Lm^-T u.  Then K = Lk Lk^T for the
         // static part (and for the "K is not positive definite" diagnosis, which wins over the modal codes).
         int sw = 0;
-        if (A.do_modal) {
+        // narrow band: every thread keeps its column of K in registers, so that K and M are factored at the same
+        // time (threads 0 and 32) instead of one after the other
+        const bool early_k = A.do_modal && P.hbw <= KCOL_HB && n <= nt;
+        double kcol[2 * KCOL_HB + 1];
+        if (early_k) {
+            load_k_column(P, smem + L.Kb, kcol, tid);
+            __syncthreads();
+            factor(true, true);
+            if (s_flag[0] != 0) {
+                fail_all(s_flag[0]);
+                return;
+            }
+        } else if (A.do_modal) {
             factor(false, true);
+        }
+        if (A.do_modal) {
             if (s_flag[1] == 0) {
                 double* s_W = smem + L.U;
-                stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
+                stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt, early_k ? &kcol : nullptr);
                 sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
                 if (sw != INT_MIN) {
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
@@ -854,7 +868,7 @@ k_solve(PlanDev P, BatchArgs A) {
                 __syncthreads();
             }
         }
-        factor(true, false);
+        if (!early_k) factor(true, false);
         const int infoK = s_flag[0], infoM = s_flag[1];
         if (infoK != 0 || infoM != 0 || sw == INT_MIN) {
             fail_all(infoK != 0 ? infoK : (infoM != 0 ? -1 : -2));

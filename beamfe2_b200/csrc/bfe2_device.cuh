@@ -904,16 +904,38 @@ __device__ __forceinline__ int stage_jacobi_regs(const PlanDev& P, double* s_W, 
 // column j of C.  Two passes of band forward substitutions with the factor Lm of M: thread j turns column j of K
 // (read from its unfactored band) into column j of X = Lm^-1 K; then thread i turns row i of X into row i of
 // C = X Lm^-T (a substitution along the slots, stride LD).
+// Column `tid` of the band matrix K (rows tid - b .. tid + b) into registers, before K is factored in place.
+constexpr int KCOL_HB = 8;
+__device__ __forceinline__ void load_k_column(const PlanDev& P, const double* s_Kb, double (&kcol)[2 * KCOL_HB + 1],
+                                              int tid) {
+    const int n = P.n, b = P.hbw;
+#pragma unroll
+    for (int d = -KCOL_HB; d <= KCOL_HB; ++d) {
+        const int i = tid + d;
+        const bool in = tid < n && d >= -b && d <= b && i >= 0 && i < n;
+        kcol[d + KCOL_HB] = in ? (d < 0 ? s_Kb[(-d) * n + i] : s_Kb[d * n + tid]) : 0.0;
+    }
+}
+
+// kcol != nullptr: the columns of K come from the registers filled by load_k_column (needs n <= blockDim and
+// hbw <= KCOL_HB), s_Kb may already hold the factor of K.
 __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_Kb, const double* s_Mb,
-                                             const double* s_invM, double* s_W, int tid, int nt) {
+                                             const double* s_invM, double* s_W, int tid, int nt,
+                                             const double (*kcol)[2 * KCOL_HB + 1] = nullptr) {
     const int n = P.n, b = P.hbw, LD = P.LD;
     for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
     __syncthreads();
     for (int j = tid; j < n; j += nt) {
         double* col = s_W + j * LD;
         const int lo = max(0, j - b), hi = min(n - 1, j + b);
-        for (int i = lo; i < j; ++i) col[i] = s_Kb[(j - i) * n + i];
-        for (int i = j; i <= hi; ++i) col[i] = s_Kb[(i - j) * n + j];
+        if (kcol != nullptr) {
+#pragma unroll
+            for (int d = -KCOL_HB; d <= KCOL_HB; ++d)
+                if (j + d >= lo && j + d <= hi) col[j + d] = (*kcol)[d + KCOL_HB];
+        } else {
+            for (int i = lo; i < j; ++i) col[i] = s_Kb[(j - i) * n + i];
+            for (int i = j; i <= hi; ++i) col[i] = s_Kb[(i - j) * n + j];
+        }
         if (b <= 5) band_subst_thread<5, true, false>(s_Mb, s_invM, col, 1, n, b, lo);
         else if (b <= 8) band_subst_thread<8, true, false>(s_Mb, s_invM, col, 1, n, b, lo);
         else {
