@@ -102,6 +102,46 @@ def test_small_dense_eig_vs_scipy():
     assert np.abs(A @ V.T - B @ V.T * lam[None, :]).max() / np.abs(A).max() < 1e-11
 
 
+@pytest.mark.parametrize('n', [7, 24, 40, 58])
+def test_dense_eig_register_path(n):
+    """bfe2_sym_eig_dense for n <= 58: the register-resident Jacobi path with the pivoted-Cholesky preconditioner
+    on a full (not banded) pencil; a batch of graded matrices, one of them with an indefinite A."""
+    import ctypes as C
+    from beamfe2_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(n)
+    nb = 4
+    A = np.empty((nb, n, n))
+    Bm = np.empty((nb, n, n))
+    for b in range(nb):
+        R1, R2 = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+        D = np.diag(np.logspace(0, 2 * b, n))                           # graded: cond up to 1e6 * cond(R1 R1^T)
+        A[b] = D @ (R1 @ R1.T + n * np.eye(n)) @ D
+        Bm[b] = R2 @ R2.T + n * np.eye(n)
+    A[3] = -A[3]                                                        # not positive definite
+    h = C.c_void_p()
+    _lib.check(L.bfe2_plan_create_dense(C.byref(h), n))
+    tA, tB = torch.as_tensor(A, device=DEV), torch.as_tensor(Bm, device=DEV)
+    lam = torch.empty((nb, n), dtype=torch.float64, device=DEV)
+    V = torch.empty((nb, n, n), dtype=torch.float64, device=DEV)
+    info = torch.zeros(nb, dtype=torch.int32, device=DEV)
+    sw = torch.zeros(nb, dtype=torch.int32, device=DEV)
+    ws = torch.empty(nb * 2 * n * n, dtype=torch.float64, device=DEV)
+    _lib.check(L.bfe2_sym_eig_dense(h, nb, _lib.ptr(tA), _lib.ptr(tB), _lib.ptr(lam), _lib.ptr(V), _lib.ptr(info),
+                                    _lib.ptr(sw), _lib.ptr(ws), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    L.bfe2_plan_destroy(h)
+    info = info.cpu().numpy()
+    assert (info[:3] == 0).all() and info[3] > 0 and torch.isnan(lam[3]).all()
+    assert (sw[:3].cpu().numpy() <= 12).all()
+    for b in range(3):
+        w = sla.eigh(A[b], Bm[b], eigvals_only=True)
+        l, v = lam[b].cpu().numpy(), V[b].cpu().numpy()
+        assert (np.abs(l / w - 1) < 1e-11 + 64 * np.finfo(float).eps * w[-1] / w).all()
+        assert np.abs(v @ Bm[b] @ v.T - np.eye(n)).max() < 1e-10
+        assert np.abs(A[b] @ v.T - Bm[b] @ v.T * l[None, :]).max() / np.abs(A[b]).max() < 1e-11
+
+
 @pytest.mark.parametrize('n_elem', [300, 2000])
 def test_modal_subspace_iteration(n_elem):
     length = 1000.0

@@ -282,6 +282,10 @@ def test_failure_reporting_and_edge_cases():
     neg[..., 0] = -neg[..., 0]
     out = batch.solve_fused(plan, pk['coords'], neg, pk['nodal_mass'], pk['f_nodal'], pk['r_local'], modal=False)
     assert (out['info'] == 1).all() and torch.isnan(out['u']).all() and torch.isnan(out['reactions']).all()
+    out = batch.solve_fused(plan, pk['coords'], neg, pk['nodal_mass'], pk['f_nodal'], pk['r_local'], n_modes=3)
+    assert (out['info'] == 1).all() and torch.isnan(out['u']).all() and torch.isnan(out['lam']).all()
+    out = batch.solve_fused(plan, pk['coords'], neg, pk['nodal_mass'], None, None, n_modes=3)      # modal only
+    assert (out['info'] == 1).all() and torch.isnan(out['lam']).all() and torch.isnan(out['phi']).all()
     free_plan = Plan(21, conn, [])
     out = batch.solve_fused(free_plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
                             modal=False)
