@@ -1051,6 +1051,7 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
     p->npad = p->n + (p->n & 1);
     if (p->n > 0 && jacobi_config(p->n, &p->rpl, &p->lpp)) {
         p->LD = p->rpl * p->lpp;
+        if (p->n <= 58) p->LD |= 1;               // register path: odd slot pitch, thread-per-slot access is conflict-free
         p->nthreads = std::max(64, ((p->npad / 2) * p->lpp + 31) / 32 * 32);
     } else {
         p->rpl = p->lpp = 0;          // static / assembly still work; modal is refused
@@ -1253,6 +1254,7 @@ int bfe2_plan_create_dense(bfe2_plan** out, int32_t n) {
     p->npad = n + (n & 1);
     jacobi_config(n, &p->rpl, &p->lpp);
     p->LD = p->rpl * p->lpp;
+    if (p->n <= 58) p->LD |= 1;
     p->nthreads = 64;
     *out = p;
     return 0;
