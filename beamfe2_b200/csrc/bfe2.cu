@@ -74,10 +74,6 @@ namespace {
 
 // Jacobi lane configuration for n free DOFs: RPL rows per lane, LPP lanes per column pair.
 bool jacobi_config(int n, int* rpl, int* lpp) {
-    // BFE2_NW = 3 | 4: experimental row split over 3 / 4 warps per structure (register-resident variant)
-    static const int nw = [] { const char* e = getenv("BFE2_NW"); return e ? atoi(e) : 0; }();
-    if (nw == 3 && n > 30 && n <= 57) { *rpl = 19; *lpp = 3; return true; }
-    if (nw == 4 && n > 30 && n <= 60) { *rpl = 15; *lpp = 4; return true; }
     if (n <= 10) { *rpl = 5; *lpp = 2; return true; }
     if (n <= 30) { *rpl = 15; *lpp = 2; return true; }
     if (n <= 58) { *rpl = 29; *lpp = 2; return true; }
@@ -735,20 +731,10 @@ int launch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream
 // 0: launched; 1: this plan does not fit the group kernel (wide band / too much shared memory); < 0: error
 template <bool ASSEMBLE>
 int dispatch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
-    static const int G = [] { const char* e = getenv("BFE2_STATIC_G"); return e ? atoi(e) : 16; }();
-    if (G == 0 || plan->hbw > 8 || plan->nE == 0) return 1;
-#define BFE2_SG(GG, HH) launch_static_group<GG, HH, ASSEMBLE>(plan, A, stream)
-    if (plan->hbw <= 5) {
-        if (G == 4) return BFE2_SG(4, 5);
-        if (G == 16) return BFE2_SG(16, 5);
-        if (G == 32) return BFE2_SG(32, 5);
-        return BFE2_SG(8, 5);
-    }
-    if (G == 4) return BFE2_SG(4, 8);
-    if (G == 16) return BFE2_SG(16, 8);
-    if (G == 32) return BFE2_SG(32, 8);
-    return BFE2_SG(8, 8);
-#undef BFE2_SG
+    // 16 lanes per structure: measured best of 4 / 8 / 16 / 32 (profiles/r1_ablation.md)
+    if (plan->hbw > 8 || plan->nE == 0) return 1;
+    return plan->hbw <= 5 ? launch_static_group<16, 5, ASSEMBLE>(plan, A, stream)
+                          : launch_static_group<16, 8, ASSEMBLE>(plan, A, stream);
 }
 
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
@@ -920,21 +906,15 @@ int launch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
 
 template <bool ASSEMBLE>
 int dispatch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
-    // n <= 58: register-resident odd-even Jacobi (two warps per structure); BFE2_JACOBI=smem selects the
-    // shared-memory round-robin variant for A/B measurements.  58 < n <= 116: shared-memory variant.
-    static const bool use_smem = [] { const char* e = getenv("BFE2_JACOBI"); return e && !strcmp(e, "smem"); }();
-    if (plan->rpl == 19 && plan->lpp == 3) return launch_solve<19, 3, 96, 5, ASSEMBLE, true>(plan, A, stream);
-    if (plan->rpl == 15 && plan->lpp == 4) return launch_solve<15, 4, 128, 5, ASSEMBLE, true>(plan, A, stream);
-    if (plan->lpp == 2 && !use_smem) {
+    // n <= 58: register-resident, preconditioned odd-even Jacobi (two warps per structure);
+    // 58 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
+    if (plan->lpp == 2) {
         if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
         if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
         // __launch_bounds__(64, 5): same 168 registers and 6 resident blocks as (64, 6), but ptxas schedules the
         // software-pipelined step better (+4.7 % measured); (64, 4) takes 216 registers, 4 blocks and is slower.
         if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, A, stream);
     }
-    if (plan->rpl == 5 && plan->lpp == 2) return launch_solve<5, 2, 64, 8, ASSEMBLE, false>(plan, A, stream);
-    if (plan->rpl == 15 && plan->lpp == 2) return launch_solve<15, 2, 64, 8, ASSEMBLE, false>(plan, A, stream);
-    if (plan->rpl == 29 && plan->lpp == 2) return launch_solve<29, 2, 64, 6, ASSEMBLE, false>(plan, A, stream);
     if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
