@@ -273,11 +273,30 @@ k_element_km(long long nE, const double* __restrict__ xi, const double* __restri
     }
 }
 
+// Beam stiffness and consistent mass in global axes in closed form (T X T^T, HermitianBeam_2D.py:173-175, of the
+// local matrices :284-297 and :233-249): seven resp. twelve distinct numbers per beam,
+//   K: p = a c^2 + b12 s^2, q = (a - b12) c s, r = a s^2 + b12 c^2, t = b6 s, w = b6 c, b4, b2
+//   M: f = rho A L / 420;  ii/jj block: f (140 c^2 + 156 s^2), -16 f c s, f (140 s^2 + 156 c^2), 22 L f s, 22 L f c,
+//      4 L^2 f;  ij block: f (70 c^2 + 54 s^2), 16 f c s, f (70 s^2 + 54 c^2), 13 L f s, 13 L f c, -3 L^2 f
+// c_ke7 / c_me12 [6 r + c] = +-(1 + index of the number that entry (r, c) of the 6 x 6 matrix equals).
+__constant__ signed char c_ke7[36] = {+1, +2, -4, -1, -2, -4,
+                                      +2, +3, +5, -2, -3, +5,
+                                      -4, +5, +6, +4, -5, +7,
+                                      -1, -2, +4, +1, +2, +4,
+                                      -2, -3, -5, +2, +3, -5,
+                                      -4, +5, +7, +4, -5, +6};
+__constant__ signed char c_me12[36] = {+1, +2, -4, +7, +8, +10,
+                                       +2, +3, +5, +8, +9, -11,
+                                       -4, +5, +6, -10, +11, +12,
+                                       +7, +8, -10, +1, +2, +4,
+                                       +8, +9, +11, +2, +3, -5,
+                                       +10, -11, +12, +4, -5, +6};
+
 // ---- K2: WARP-PER-STRUCTURE assembly: bands to HBM.  The integer plan is cached once per block in shared
-//      memory (blocks are persistent: grid-stride over structures), every warp stages its structure's inputs
-//      and the 2 x nE element matrices in its own shared-memory slice, then each lane owns band slots
-//      lane, lane+32, ... and adds their contributions in beam order (no atomics); the sums go straight to HBM
-//      as coalesced 8-byte stores.  Only __syncwarp inside the loop.
+//      memory, its contributions already decoded to (beam, number, sign); blocks are persistent (grid-stride over
+//      structures).  A lane works out the 7 + 12 numbers of its beams straight from the structure's record, then
+//      each lane owns band slots lane, lane+32, ... and adds their contributions in beam order (no atomics); the
+//      sums go straight to HBM as coalesced 8-byte stores.  160 B of shared memory per beam: 64 warps per SM.
 constexpr int K2_WARPS = 8;
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
@@ -285,64 +304,94 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mass = A.Mb_out != nullptr;
-    // block-shared plan cache (int32)
-    const int per_warp = 4 * P.nN + 4 * P.nE + 72 * P.nE;                 // doubles
+    const int per_warp = 20 * P.nE;                                        // doubles: [nE][8] K numbers, [nE][12] M
     const int nw = blockDim.x >> 5;                                        // warps (= structures in flight) per block
     int* c_conn = reinterpret_cast<int*>(smem + (size_t)nw * per_warp);
     int* c_pos = c_conn + 2 * P.nE;
     int* c_ptr = c_pos + P.n;
-    int* c_con = c_ptr + P.nslots + 1;
-    int* c_lump = c_con + ncontrib;
+    int* c_conk = c_ptr + P.nslots + 1;
+    int* c_conm = c_conk + ncontrib;
+    int* c_lump = c_conm + ncontrib;
     for (int i = tid; i < 2 * P.nE; i += blockDim.x) c_conn[i] = P.conn[i];
     for (int i = tid; i < P.n; i += blockDim.x) c_pos[i] = P.pos_of_free[i];
     for (int i = tid; i <= P.nslots; i += blockDim.x) c_ptr[i] = P.slot_ptr[i];
-    for (int i = tid; i < ncontrib; i += blockDim.x) c_con[i] = P.contrib[i];
+    for (int i = tid; i < ncontrib; i += blockDim.x) {
+        const int idx = P.contrib[i], e = idx / 36;
+        const int ck = c_ke7[idx % 36], cm = c_me12[idx % 36];
+        c_conk[i] = (e * 8 + (ck < 0 ? -ck : ck) - 1) | (ck < 0 ? (int)0x80000000 : 0);
+        c_conm[i] = (e * 12 + (cm < 0 ? -cm : cm) - 1) | (cm < 0 ? (int)0x80000000 : 0);
+    }
     for (int i = tid; i < P.nE; i += blockDim.x) c_lump[i] = P.lumped[i];
     __syncthreads();
-    double* w_coords = smem + (size_t)warp * per_warp;
-    double* w_props = w_coords + 2 * P.nN;
-    double* w_mass = w_props + 4 * P.nE;
-    double* w_Ke = w_mass + 2 * P.nN;
-    double* w_Me = w_Ke + 36 * P.nE;
+    double* w_k = smem + (size_t)warp * per_warp;
+    double* w_m = w_k + 8 * P.nE;
     const long long nwarps = (long long)gridDim.x * nw;
     for (long long b = (long long)blockIdx.x * nw + warp; b < A.B; b += nwarps) {
-        for (int i = lane; i < 2 * P.nN; i += 32) w_coords[i] = A.coords[b * 2 * P.nN + i];
-        for (int i = lane; i < 4 * P.nE; i += 32) w_props[i] = A.props[b * 4 * P.nE + i];
-        if (A.nodal_mass != nullptr)
-            for (int i = lane; i < 2 * P.nN; i += 32) w_mass[i] = A.nodal_mass[b * 2 * P.nN + i];
-        __syncwarp();
-        const int items = want_mass ? 2 * P.nE : P.nE;
-        for (int it = lane; it < items; it += 32) {
-            const int e = it < P.nE ? it : it - P.nE;
-            const bool mass = it >= P.nE;
+        const double* g_coords = A.coords + b * 2 * P.nN;
+        const double* g_props = A.props + b * 4 * P.nE;
+        for (int e = lane; e < P.nE; e += 32) {
             const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
-            double L, c, s;
-            beam_geometry(w_coords[2 * ni], w_coords[2 * ni + 1], w_coords[2 * nj], w_coords[2 * nj + 1], L, c, s);
-            double X[6][6];
-            if (!mass) ke_local(X, w_props[4 * e], w_props[4 * e + 1], w_props[4 * e + 2], L);
-            else me_local(X, w_props[4 * e + 3], w_props[4 * e + 1], L, c_lump[e] != 0);
-            rotate_to_global(X, c, s);
-            double* dst = (mass ? w_Me : w_Ke) + 36 * e;
+            const double dx = g_coords[2 * nj] - g_coords[2 * ni], dy = g_coords[2 * nj + 1] - g_coords[2 * ni + 1];
+            const double E = g_props[4 * e], Ar = g_props[4 * e + 1], I = g_props[4 * e + 2], rho = g_props[4 * e + 3];
+            const double d2 = fma(dx, dx, dy * dy);
+            const double iL = rsqrt_fast(d2), L = d2 * iL;
+            const double cs = dx * iL, sn = dy * iL;
+            const double a = (E * Ar) * iL, eil = (E * I) * iL;
+            const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL;
+            double* k7 = w_k + 8 * e;
+            k7[0] = fma(a * cs, cs, (b12 * sn) * sn);
+            k7[1] = ((a - b12) * cs) * sn;
+            k7[2] = fma(a * sn, sn, (b12 * cs) * cs);
+            k7[3] = b6 * sn;
+            k7[4] = b6 * cs;
+            k7[5] = 4.0 * eil;
+            k7[6] = 2.0 * eil;
+            if (want_mass) {
+                double* m12 = w_m + 12 * e;
+                if (c_lump[e] != 0) {                 // HermitianBeam_2D.py:225-231: m on translations, m 1e-10 on rotations
+                    const double m = 0.5 * Ar * L * rho;
+                    m12[0] = m; m12[1] = 0.0; m12[2] = m; m12[3] = 0.0; m12[4] = 0.0; m12[5] = m * 1e-10;
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int q = 0; q < 6; ++q) dst[6 * r + q] = X[r][q];
+                    for (int k = 6; k < 12; ++k) m12[k] = 0.0;
+                } else {
+                    const double f = rho * Ar * L / 420.0, fl = f * L;
+                    const double cc = cs * cs, ss = sn * sn, fcs = (f * cs) * sn;
+                    m12[0] = f * fma(140.0, cc, 156.0 * ss);
+                    m12[1] = -16.0 * fcs;
+                    m12[2] = f * fma(140.0, ss, 156.0 * cc);
+                    m12[3] = (22.0 * fl) * sn;
+                    m12[4] = (22.0 * fl) * cs;
+                    m12[5] = (4.0 * fl) * L;
+                    m12[6] = f * fma(70.0, cc, 54.0 * ss);
+                    m12[7] = 16.0 * fcs;
+                    m12[8] = f * fma(70.0, ss, 54.0 * cc);
+                    m12[9] = (13.0 * fl) * sn;
+                    m12[10] = (13.0 * fl) * cs;
+                    m12[11] = (-3.0 * fl) * L;
+                }
+            }
         }
         __syncwarp();
+        const double* g_mass = A.nodal_mass ? A.nodal_mass + b * 2 * P.nN : nullptr;
         for (int slot = lane; slot < P.nslots; slot += 32) {
             const int p0 = c_ptr[slot], p1 = c_ptr[slot + 1];
             double k = 0.0, m = 0.0;
             for (int p = p0; p < p1; ++p) {
-                const int idx = c_con[p];
-                k += w_Ke[idx];
-                if (want_mass) m += w_Me[idx];
+                const int ck = c_conk[p];
+                const double vk = w_k[ck & 0x7fffffff];
+                k += (ck < 0) ? -vk : vk;
+                if (want_mass) {
+                    const int cm = c_conm[p];
+                    const double vm = w_m[cm & 0x7fffffff];
+                    m += (cm < 0) ? -vm : vm;
+                }
             }
             A.Kb_out[b * P.nslots + slot] = k;
             if (want_mass) {
-                if (slot < P.n && A.nodal_mass != nullptr) {
+                if (slot < P.n && g_mass != nullptr) {
                     const int pos = c_pos[slot];
                     const int dof = pos % 3;
-                    if (dof < 2) m += w_mass[2 * (pos / 3) + dof];
+                    if (dof < 2) m += g_mass[2 * (pos / 3) + dof];
                 }
                 A.Mb_out[b * P.nslots + slot] = m;
             }
@@ -421,12 +470,6 @@ k_static_warp(PlanDev P, BatchArgs A) {
 //   HermitianBeam_2D.py:173-175 / :284-297):
 //     p = a c^2 + b12 s^2, q = (a - b12) c s, r = a s^2 + b12 c^2, t = b6 s, w = b6 c, b4, b2
 //   c_ke7[6 r + c] = +-(1 + index into {p,q,r,t,w,b4,b2}).
-__constant__ signed char c_ke7[36] = {+1, +2, -4, -1, -2, -4,
-                                      +2, +3, +5, -2, -3, +5,
-                                      -4, +5, +6, +4, -5, +7,
-                                      -1, -2, +4, +1, +2, +4,
-                                      -2, -3, -5, +2, +3, -5,
-                                      -4, +5, +7, +4, -5, +6};
 
 struct GroupLayout { int a, kb, per_group; };
 
@@ -1116,8 +1159,8 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     if (int r = plan_upload(plan)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
-    const size_t per_warp = (size_t)(4 * plan->nN + 4 * plan->nE + 72 * plan->nE) * sizeof(double);
-    const size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + plan->ncontrib + plan->nE) * sizeof(int) + 16;
+    const size_t per_warp = (size_t)(20 * plan->nE) * sizeof(double);
+    const size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + 2 * plan->ncontrib + plan->nE) * sizeof(int) + 16;
     int nw = K2_WARPS;                                 // fewer warps per block when a structure's slice is large
     while (nw > 1 && nw * per_warp + cache > 110 * 1024) --nw;
     const size_t bytes = nw * per_warp + cache;

@@ -253,8 +253,19 @@ def test_modal_unfused_equals_fused():
     Kb, Mb = batch.assemble_banded(plan, pk['coords'], pk['props'], pk['nodal_mass'])
     m = batch.modal_solve(plan, Kb, Mb, n_modes=10)
     f = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'], n_modes=10)
-    for k in ('lam', 'phi', 'info', 'sweeps'):
-        assert torch.equal(m[k], f[k]), k
+    # K2 forms the beam matrices in closed form, the fused kernel by the reference's two 6 x 6 products: the bands
+    # differ in the last bit, the results within the rounding amplification of the eigenproblem
+    assert torch.equal(m['info'], f['info'])
+    lam_m, lam_f = m['lam'].cpu().numpy(), f['lam'].cpu().numpy()
+    assert (np.abs(lam_m / lam_f - 1) < 1e-11 + 64 * EPS * lam_f[:, -1:] / lam_f).all()
+    keep = plan.pos_of_free
+    for b in range(0, 200, 40):                                         # mode shapes: sign-free, gap-scaled
+        pm, pf = m['phi'][b].cpu().numpy()[:, keep], f['phi'][b].cpu().numpy()[:, keep]
+        gap = np.minimum(np.diff(lam_f[b][:11]), np.r_[np.inf, np.diff(lam_f[b][:10])])
+        tol = 1e-10 + 256 * EPS * lam_f[b, -1] / gap
+        pm = pm * np.sign(np.sum(pm * pf, axis=1))[:, None]            # largest-entry sign rule can tie
+        err = np.abs(pm - pf).max(axis=1) / np.abs(pf).max(axis=1)
+        assert (err < tol).all(), (b, err, tol)
 
 
 def test_rod30_analytic_and_lumped():
