@@ -60,6 +60,7 @@ struct bfe2_plan {
     int nN = 0, nE = 0, sumdof = 0, n = 0, hbw = 0, nslots = 0, ncontrib = 0;
     int npad = 0, LD = 0, rpl = 0, lpp = 0, nthreads = 0;
     std::vector<int32_t> conn, free_of_pos, pos_of_free, fixed, slot_ptr, contrib, node_ptr, node_inc;
+    std::vector<int32_t> contrib_k, contrib_m;   // contrib decoded: beam*8 + K number | beam*12 + M number, sign in bit 31
     std::vector<uint8_t> lumped;
     // device mirror: uploaded lazily on the first launch on a device; one copy per device is kept (a plan may be
     // used from several devices, e.g. one thread per GPU), `dev` always describes the CURRENT device's copy
@@ -144,17 +145,18 @@ int plan_upload(bfe2_plan* p) {
         }
     }
     // one blob: all int32 arrays then the uint8 flags
-    const std::vector<int32_t>* arrs[7] = {&p->conn, &p->free_of_pos, &p->pos_of_free, &p->slot_ptr,
-                                           &p->contrib, &p->node_ptr, &p->node_inc};
-    size_t off[8];
+    constexpr int NA = 9;
+    const std::vector<int32_t>* arrs[NA] = {&p->conn, &p->free_of_pos, &p->pos_of_free, &p->slot_ptr, &p->contrib,
+                                            &p->node_ptr, &p->node_inc, &p->contrib_k, &p->contrib_m};
+    size_t off[NA + 1];
     size_t tot = 0;
-    for (int i = 0; i < 7; ++i) { off[i] = tot; tot += ((arrs[i]->size() + 3) & ~size_t(3)); }
-    off[7] = tot;
+    for (int i = 0; i < NA; ++i) { off[i] = tot; tot += ((arrs[i]->size() + 3) & ~size_t(3)); }
+    off[NA] = tot;
     const size_t bytes = tot * sizeof(int32_t) + ((p->lumped.size() + 15) & ~size_t(15));
     std::vector<unsigned char> host(bytes, 0);
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < NA; ++i)
         if (!arrs[i]->empty()) memcpy(host.data() + off[i] * 4, arrs[i]->data(), arrs[i]->size() * 4);
-    if (!p->lumped.empty()) memcpy(host.data() + off[7] * 4, p->lumped.data(), p->lumped.size());
+    if (!p->lumped.empty()) memcpy(host.data() + off[NA] * 4, p->lumped.data(), p->lumped.size());
     BFE2_CUDA(cudaMalloc(&p->d_blob, bytes));
     BFE2_CUDA(cudaMemcpy(p->d_blob, host.data(), bytes, cudaMemcpyHostToDevice));
     const int32_t* base = static_cast<const int32_t*>(p->d_blob);
@@ -168,7 +170,9 @@ int plan_upload(bfe2_plan* p) {
     d.contrib = base + off[4];
     d.node_ptr = base + off[5];
     d.node_inc = base + off[6];
-    d.lumped = reinterpret_cast<const uint8_t*>(base + off[7]);
+    d.contrib_k = base + off[7];
+    d.contrib_m = base + off[8];
+    d.lumped = reinterpret_cast<const uint8_t*>(base + off[NA]);
     p->uploaded = true;
     p->device = dev;
     p->copies[dev] = std::make_pair(p->d_blob, p->dev);
@@ -278,20 +282,8 @@ k_element_km(long long nE, const double* __restrict__ xi, const double* __restri
 //   K: p = a c^2 + b12 s^2, q = (a - b12) c s, r = a s^2 + b12 c^2, t = b6 s, w = b6 c, b4, b2
 //   M: f = rho A L / 420;  ii/jj block: f (140 c^2 + 156 s^2), -16 f c s, f (140 s^2 + 156 c^2), 22 L f s, 22 L f c,
 //      4 L^2 f;  ij block: f (70 c^2 + 54 s^2), 16 f c s, f (70 s^2 + 54 c^2), 13 L f s, 13 L f c, -3 L^2 f
-// c_ke7 / c_me12 [6 r + c] = +-(1 + index of the number that entry (r, c) of the 6 x 6 matrix equals).
-__constant__ signed char c_ke7[36] = {+1, +2, -4, -1, -2, -4,
-                                      +2, +3, +5, -2, -3, +5,
-                                      -4, +5, +6, +4, -5, +7,
-                                      -1, -2, +4, +1, +2, +4,
-                                      -2, -3, -5, +2, +3, -5,
-                                      -4, +5, +7, +4, -5, +6};
-__constant__ signed char c_me12[36] = {+1, +2, -4, +7, +8, +10,
-                                       +2, +3, +5, +8, +9, -11,
-                                       -4, +5, +6, -10, +11, +12,
-                                       +7, +8, -10, +1, +2, +4,
-                                       +8, +9, +11, +2, +3, -5,
-                                       +10, -11, +12, +4, -5, +6};
-
+// The plan carries, for every contribution e*36 + 6 r + c, which of these numbers entry (r, c) equals and its sign
+// (h_ke7 / h_me12 in the plan builder).
 // ---- K2: WARP-PER-STRUCTURE assembly: bands to HBM.  The integer plan is cached once per block in shared
 //      memory, its contributions already decoded to (beam, number, sign); blocks are persistent (grid-stride over
 //      structures).  A lane works out the 7 + 12 numbers of its beams straight from the structure's record, then
@@ -315,12 +307,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
     for (int i = tid; i < 2 * P.nE; i += blockDim.x) c_conn[i] = P.conn[i];
     for (int i = tid; i < P.n; i += blockDim.x) c_pos[i] = P.pos_of_free[i];
     for (int i = tid; i <= P.nslots; i += blockDim.x) c_ptr[i] = P.slot_ptr[i];
-    for (int i = tid; i < ncontrib; i += blockDim.x) {
-        const int idx = P.contrib[i], e = idx / 36;
-        const int ck = c_ke7[idx % 36], cm = c_me12[idx % 36];
-        c_conk[i] = (e * 8 + (ck < 0 ? -ck : ck) - 1) | (ck < 0 ? (int)0x80000000 : 0);
-        c_conm[i] = (e * 12 + (cm < 0 ? -cm : cm) - 1) | (cm < 0 ? (int)0x80000000 : 0);
-    }
+    for (int i = tid; i < ncontrib; i += blockDim.x) { c_conk[i] = P.contrib_k[i]; c_conm[i] = P.contrib_m[i]; }
     for (int i = tid; i < P.nE; i += blockDim.x) c_lump[i] = P.lumped[i];
     __syncthreads();
     double* w_k = smem + (size_t)warp * per_warp;
@@ -331,45 +318,10 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
         const double* g_props = A.props + b * 4 * P.nE;
         for (int e = lane; e < P.nE; e += 32) {
             const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
-            const double dx = g_coords[2 * nj] - g_coords[2 * ni], dy = g_coords[2 * nj + 1] - g_coords[2 * ni + 1];
-            const double E = g_props[4 * e], Ar = g_props[4 * e + 1], I = g_props[4 * e + 2], rho = g_props[4 * e + 3];
-            const double d2 = fma(dx, dx, dy * dy);
-            const double iL = rsqrt_fast(d2), L = d2 * iL;
-            const double cs = dx * iL, sn = dy * iL;
-            const double a = (E * Ar) * iL, eil = (E * I) * iL;
-            const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL;
-            double* k7 = w_k + 8 * e;
-            k7[0] = fma(a * cs, cs, (b12 * sn) * sn);
-            k7[1] = ((a - b12) * cs) * sn;
-            k7[2] = fma(a * sn, sn, (b12 * cs) * cs);
-            k7[3] = b6 * sn;
-            k7[4] = b6 * cs;
-            k7[5] = 4.0 * eil;
-            k7[6] = 2.0 * eil;
-            if (want_mass) {
-                double* m12 = w_m + 12 * e;
-                if (c_lump[e] != 0) {                 // HermitianBeam_2D.py:225-231: m on translations, m 1e-10 on rotations
-                    const double m = 0.5 * Ar * L * rho;
-                    m12[0] = m; m12[1] = 0.0; m12[2] = m; m12[3] = 0.0; m12[4] = 0.0; m12[5] = m * 1e-10;
-#pragma unroll
-                    for (int k = 6; k < 12; ++k) m12[k] = 0.0;
-                } else {
-                    const double f = rho * Ar * L / 420.0, fl = f * L;
-                    const double cc = cs * cs, ss = sn * sn, fcs = (f * cs) * sn;
-                    m12[0] = f * fma(140.0, cc, 156.0 * ss);
-                    m12[1] = -16.0 * fcs;
-                    m12[2] = f * fma(140.0, ss, 156.0 * cc);
-                    m12[3] = (22.0 * fl) * sn;
-                    m12[4] = (22.0 * fl) * cs;
-                    m12[5] = (4.0 * fl) * L;
-                    m12[6] = f * fma(70.0, cc, 54.0 * ss);
-                    m12[7] = 16.0 * fcs;
-                    m12[8] = f * fma(70.0, ss, 54.0 * cc);
-                    m12[9] = (13.0 * fl) * sn;
-                    m12[10] = (13.0 * fl) * cs;
-                    m12[11] = (-3.0 * fl) * L;
-                }
-            }
+            double L, cs, sn;
+            beam_numbers(g_coords[2 * ni], g_coords[2 * ni + 1], g_coords[2 * nj], g_coords[2 * nj + 1], g_props[4 * e],
+                         g_props[4 * e + 1], g_props[4 * e + 2], g_props[4 * e + 3], want_mass, c_lump[e] != 0,
+                         w_k + 8 * e, w_m + 12 * e, L, cs, sn);
         }
         __syncwarp();
         const double* g_mass = A.nodal_mass ? A.nodal_mass + b * 2 * P.nN : nullptr;
@@ -518,11 +470,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
     for (int i = tid; i <= nN; i += blockDim.x) c_nptr[i] = P.node_ptr[i];
     if (ASSEMBLE) {
         for (int i = tid; i <= nslots; i += blockDim.x) c_sptr[i] = P.slot_ptr[i];
-        for (int i = tid; i < ncontrib; i += blockDim.x) {
-            const int idx = P.contrib[i];
-            const int code = c_ke7[idx % 36];
-            c_con[i] = ((idx / 36) * 8 + (code < 0 ? -code : code) - 1) | (code < 0 ? (int)0x80000000 : 0);
-        }
+        for (int i = tid; i < ncontrib; i += blockDim.x) c_con[i] = P.contrib_k[i];
     }
     __syncthreads();
     double* s_geo = smem + (size_t)gi * GL.per_group;            // [nE][5] = 1/L, cos, sin, EA/L, EI/L
@@ -808,12 +756,12 @@ k_solve(PlanDev P, BatchArgs A) {
     if (tid < 2) s_flag[tid] = 0;
     __syncthreads();
     if (ASSEMBLE) {
-        stage_elements(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 36 * P.nE,
-                       A.do_modal != 0, tid, nt);
+        stage_elements_cf(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 8 * P.nE,
+                          A.do_modal != 0, tid, nt);
         __syncthreads();
-        stage_assemble(P, smem + L.U, smem + L.U + 36 * P.nE,
-                       (A.do_modal && A.nodal_mass) ? smem + L.mass : nullptr, smem + L.Kb, smem + L.Mb,
-                       A.do_modal != 0, tid, nt);
+        stage_assemble_cf(P, smem + L.U, smem + L.U + 8 * P.nE,
+                          (A.do_modal && A.nodal_mass) ? smem + L.mass : nullptr, smem + L.Kb, smem + L.Mb,
+                          A.do_modal != 0, tid, nt);
         __syncthreads();
     } else if (A.do_static) {
         stage_geometry(P, smem + L.coords, smem + L.geo, tid, nt);
@@ -1058,6 +1006,19 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
         p->contrib.insert(p->contrib.end(), lists[s].begin(), lists[s].end());
     }
     p->ncontrib = (int)p->contrib.size();
+    // which of the 7 (K) / 12 (M) closed-form numbers of a beam entry (r, c) of its global 6 x 6 matrix equals
+    static const signed char h_ke7[36] = {+1, +2, -4, -1, -2, -4, +2, +3, +5, -2, -3, +5, -4, +5, +6, +4, -5, +7,
+                                          -1, -2, +4, +1, +2, +4, -2, -3, -5, +2, +3, -5, -4, +5, +7, +4, -5, +6};
+    static const signed char h_me12[36] = {+1, +2, -4, +7, +8, +10, +2, +3, +5, +8, +9, -11, -4, +5, +6, -10, +11, +12,
+                                           +7, +8, -10, +1, +2, +4, +8, +9, +11, +2, +3, -5, +10, -11, +12, +4, -5, +6};
+    p->contrib_k.resize(p->ncontrib);
+    p->contrib_m.resize(p->ncontrib);
+    for (int i = 0; i < p->ncontrib; ++i) {
+        const int idx = p->contrib[i], e = idx / 36;
+        const int ck = h_ke7[idx % 36], cm = h_me12[idx % 36];
+        p->contrib_k[i] = (e * 8 + std::abs(ck) - 1) | (ck < 0 ? (int32_t)0x80000000 : 0);
+        p->contrib_m[i] = (e * 12 + std::abs(cm) - 1) | (cm < 0 ? (int32_t)0x80000000 : 0);
+    }
     // node -> incident beam ends, beam order
     std::vector<std::vector<int32_t>> inc(n_nodes);
     for (int e = 0; e < n_elem; ++e) {

@@ -24,6 +24,8 @@ struct PlanDev {
     const int32_t* pos_of_free;   // [n]
     const int32_t* slot_ptr;      // [nslots+1]
     const int32_t* contrib;       // [ncontrib]  e*36 + r*6 + c
+    const int32_t* contrib_k;     // [ncontrib]  e*8 + K number, sign in bit 31 (closed-form beam matrices)
+    const int32_t* contrib_m;     // [ncontrib]  e*12 + M number, sign in bit 31
     const int32_t* node_ptr;      // [nN+1]
     const int32_t* node_inc;      // [2*nE]      e*2 + end
     const uint8_t* lumped;        // [nE]
@@ -166,34 +168,98 @@ __device__ __forceinline__ void beam_geometry(double xi, double yi, double xj, d
 // Block-level stages.  `tid`/`nt` = thread index / count inside the block.
 // ------------------------------------------------------------------------------------------------
 
-// Stage E: geometry + global 6x6 K and M of every beam into shared memory.  Work item = (beam, matrix):
-// with 2 nE <= blockDim the stiffness and mass matrices of all beams are formed concurrently.
-__device__ __forceinline__ void stage_elements(const PlanDev& P, const double* s_coords, const double* s_props,
-                                               double* s_geo, double* s_Ke, double* s_Me, bool want_mass,
-                                               int tid, int nt) {
-    const int items = want_mass ? 2 * P.nE : P.nE;
-    for (int it = tid; it < items; it += nt) {
-        const int e = it < P.nE ? it : it - P.nE;
-        const bool mass = it >= P.nE;
+// Stages E + A: beam matrices in global axes and collision-free assembly of the condensed band matrices.  Every
+// band slot (d, j) is owned by one thread which adds its contributions in beam-list order -- the summation order
+// of helpers.py:19-39 -- so no atomics and a deterministic result.  Supported rows/columns are simply not in
+// the plan (Structure.condense, Structure.py:183-191); nodal masses go on the diagonal (Structure.py:198-209;
+// mx->ux, my->uy, no rotary term :289-313).  The beam matrices are used in closed form: the rotated
+// stiffness T k T^T of a beam has 7 distinct numbers, the rotated consistent mass 12,
+//   K: p = a c^2 + b12 s^2, q = (a - b12) c s, r = a s^2 + b12 c^2, t = b6 s, w = b6 c, b4, b2
+//   M: f = rho A L / 420;  ii/jj block: f (140 c^2 + 156 s^2), -16 f c s, f (140 s^2 + 156 c^2), 22 L f s, 22 L f c,
+//      4 L^2 f;  ij block: f (70 c^2 + 54 s^2), 16 f c s, f (70 s^2 + 54 c^2), 13 L f s, 13 L f c, -3 L^2 f
+// and the plan says which of them (and with which sign) every band contribution is (contrib_k / contrib_m).
+__device__ __forceinline__ void beam_numbers(double xi, double yi, double xj, double yj, double E, double Ar, double I,
+                                             double rho, bool want_mass, bool lumped, double* k7, double* m12,
+                                             double& L, double& cs, double& sn) {
+    const double dx = xj - xi, dy = yj - yi;
+    const double d2 = fma(dx, dx, dy * dy);
+    const double iL = rsqrt_fast(d2);
+    L = d2 * iL;
+    cs = dx * iL;
+    sn = dy * iL;
+    const double a = (E * Ar) * iL, eil = (E * I) * iL;
+    const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL;
+    k7[0] = fma(a * cs, cs, (b12 * sn) * sn);
+    k7[1] = ((a - b12) * cs) * sn;
+    k7[2] = fma(a * sn, sn, (b12 * cs) * cs);
+    k7[3] = b6 * sn;
+    k7[4] = b6 * cs;
+    k7[5] = 4.0 * eil;
+    k7[6] = 2.0 * eil;
+    if (!want_mass) return;
+    if (lumped) {                                     // HermitianBeam_2D.py:225-231: m on translations, m 1e-10 on rotations
+        const double m = 0.5 * Ar * L * rho;
+        m12[0] = m; m12[1] = 0.0; m12[2] = m; m12[3] = 0.0; m12[4] = 0.0; m12[5] = m * 1e-10;
+#pragma unroll
+        for (int k = 6; k < 12; ++k) m12[k] = 0.0;
+    } else {
+        const double f = rho * Ar * L / 420.0, fl = f * L;
+        const double cc = cs * cs, ss = sn * sn, fcs = (f * cs) * sn;
+        m12[0] = f * fma(140.0, cc, 156.0 * ss);
+        m12[1] = -16.0 * fcs;
+        m12[2] = f * fma(140.0, ss, 156.0 * cc);
+        m12[3] = (22.0 * fl) * sn;
+        m12[4] = (22.0 * fl) * cs;
+        m12[5] = (4.0 * fl) * L;
+        m12[6] = f * fma(70.0, cc, 54.0 * ss);
+        m12[7] = 16.0 * fcs;
+        m12[8] = f * fma(70.0, ss, 54.0 * cc);
+        m12[9] = (13.0 * fl) * sn;
+        m12[10] = (13.0 * fl) * cs;
+        m12[11] = (-3.0 * fl) * L;
+    }
+}
+
+__device__ __forceinline__ void stage_elements_cf(const PlanDev& P, const double* s_coords, const double* s_props,
+                                                  double* s_geo, double* s_k7, double* s_m12, bool want_mass,
+                                                  int tid, int nt) {
+    for (int e = tid; e < P.nE; e += nt) {
         const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
-        double L, c, s;
-        beam_geometry(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], L, c, s);
-        const double E = s_props[4 * e], A = s_props[4 * e + 1], I = s_props[4 * e + 2], rho = s_props[4 * e + 3];
-        double X[6][6];
-        if (!mass) {
-            s_geo[3 * e] = L;
-            s_geo[3 * e + 1] = c;
-            s_geo[3 * e + 2] = s;
-            ke_local(X, E, A, I, L);
-        } else {
-            me_local(X, rho, A, L, P.lumped[e] != 0);
+        double L, cs, sn;
+        beam_numbers(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], s_props[4 * e],
+                     s_props[4 * e + 1], s_props[4 * e + 2], s_props[4 * e + 3], want_mass, P.lumped[e] != 0,
+                     s_k7 + 8 * e, s_m12 + 12 * e, L, cs, sn);
+        s_geo[3 * e] = L;
+        s_geo[3 * e + 1] = cs;
+        s_geo[3 * e + 2] = sn;
+    }
+}
+
+__device__ __forceinline__ void stage_assemble_cf(const PlanDev& P, const double* s_k7, const double* s_m12,
+                                                  const double* s_mass, double* s_Kb, double* s_Mb, bool want_mass,
+                                                  int tid, int nt) {
+    for (int slot = tid; slot < P.nslots; slot += nt) {
+        const int p0 = P.slot_ptr[slot], p1 = P.slot_ptr[slot + 1];
+        double k = 0.0, m = 0.0;
+        for (int p = p0; p < p1; ++p) {
+            const int ck = P.contrib_k[p];
+            const double vk = s_k7[ck & 0x7fffffff];
+            k += (ck < 0) ? -vk : vk;
+            if (want_mass) {
+                const int cm = P.contrib_m[p];
+                const double vm = s_m12[cm & 0x7fffffff];
+                m += (cm < 0) ? -vm : vm;
+            }
         }
-        rotate_to_global(X, c, s);
-        double* dst = (mass ? s_Me : s_Ke) + 36 * e;
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) dst[6 * r + q] = X[r][q];
+        s_Kb[slot] = k;
+        if (want_mass) {
+            if (slot < P.n && s_mass != nullptr) {       // d == 0: diagonal
+                const int pos = P.pos_of_free[slot];
+                const int dof = pos % 3;
+                if (dof < 2) m += s_mass[2 * (pos / 3) + dof];
+            }
+            s_Mb[slot] = m;
+        }
     }
 }
 
@@ -206,34 +272,6 @@ __device__ __forceinline__ void stage_geometry(const PlanDev& P, const double* s
         s_geo[3 * e] = L;
         s_geo[3 * e + 1] = c;
         s_geo[3 * e + 2] = s;
-    }
-}
-
-// Stage A: collision-free assembly of the condensed band matrices.  Every band slot (d, j) is owned
-// by one thread which adds its contributions in beam-list order -- the summation order of
-// helpers.py:19-39 -- so no atomics and a deterministic result.  Supported rows/columns are simply
-// not in the plan (Structure.condense, Structure.py:183-191); nodal masses go on the diagonal
-// (Structure.py:198-209; mx->ux, my->uy, no rotary term :289-313).
-__device__ __forceinline__ void stage_assemble(const PlanDev& P, const double* s_Ke, const double* s_Me,
-                                               const double* s_mass, double* s_Kb, double* s_Mb,
-                                               bool want_mass, int tid, int nt) {
-    for (int slot = tid; slot < P.nslots; slot += nt) {
-        const int p0 = P.slot_ptr[slot], p1 = P.slot_ptr[slot + 1];
-        double k = 0.0, m = 0.0;
-        for (int p = p0; p < p1; ++p) {
-            const int idx = P.contrib[p];
-            k += s_Ke[idx];
-            if (want_mass) m += s_Me[idx];
-        }
-        s_Kb[slot] = k;
-        if (want_mass) {
-            if (slot < P.n && s_mass != nullptr) {       // d == 0: diagonal
-                const int pos = P.pos_of_free[slot];
-                const int dof = pos % 3;
-                if (dof < 2) m += s_mass[2 * (pos / 3) + dof];
-            }
-            s_Mb[slot] = m;
-        }
     }
 }
 
