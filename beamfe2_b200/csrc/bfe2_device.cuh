@@ -76,8 +76,8 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     // one third-order step: e = 1 - a y^2,  y <- y (1 + e/2 + 3 e^2 / 8); seed error 2^-20 -> below 2^-58
     const double e = fma(-a * y, y, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    return fma(y, p * e, y);
+    const double p = fma(0.375, e, 0.5), ye = y * e;  // independent of each other: one level less than y (p e)
+    return fma(ye, p, y);
 }
 
 // ------------------------------------------------------------------------------------------------
