@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -62,13 +63,11 @@ struct bfe2_plan {
     std::vector<int32_t> conn, free_of_pos, pos_of_free, fixed, slot_ptr, contrib, node_ptr, node_inc;
     std::vector<int32_t> contrib_k, contrib_m;   // contrib decoded: beam*8 + K number | beam*12 + M number, sign in bit 31
     std::vector<uint8_t> lumped;
-    // device mirror: uploaded lazily on the first launch on a device; one copy per device is kept (a plan may be
-    // used from several devices, e.g. one thread per GPU), `dev` always describes the CURRENT device's copy
+    // device mirrors: uploaded lazily on the first launch on a device, one copy per device (a plan may be used from
+    // several devices and host threads at once, e.g. one thread per GPU); every entry point takes its own PlanDev
+    // by value under the mutex, the plan keeps no notion of a "current" device
+    std::mutex mu;
     std::map<int, std::pair<void*, PlanDev>> copies;
-    bool uploaded = false;
-    int device = -1;
-    void* d_blob = nullptr;
-    PlanDev dev{};
 };
 
 namespace {
@@ -130,19 +129,15 @@ int half_bandwidth(const bfe2_plan* p, const int32_t* conn) {
     return hbw;
 }
 
-int plan_upload(bfe2_plan* p) {
+// Device view of the plan on the CURRENT device (uploads on first use there).
+int plan_upload(bfe2_plan* p, PlanDev* out) {
     int dev = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
-    if (p->uploaded && p->device == dev) return 0;
-    {
-        auto it = p->copies.find(dev);
-        if (it != p->copies.end()) {                  // already resident on this device: switch to that copy
-            p->d_blob = it->second.first;
-            p->dev = it->second.second;
-            p->device = dev;
-            p->uploaded = true;
-            return 0;
-        }
+    std::lock_guard<std::mutex> lock(p->mu);
+    auto it = p->copies.find(dev);
+    if (it != p->copies.end()) {
+        *out = it->second.second;
+        return 0;
     }
     // one blob: all int32 arrays then the uint8 flags
     constexpr int NA = 9;
@@ -157,10 +152,14 @@ int plan_upload(bfe2_plan* p) {
     for (int i = 0; i < NA; ++i)
         if (!arrs[i]->empty()) memcpy(host.data() + off[i] * 4, arrs[i]->data(), arrs[i]->size() * 4);
     if (!p->lumped.empty()) memcpy(host.data() + off[NA] * 4, p->lumped.data(), p->lumped.size());
-    BFE2_CUDA(cudaMalloc(&p->d_blob, bytes));
-    BFE2_CUDA(cudaMemcpy(p->d_blob, host.data(), bytes, cudaMemcpyHostToDevice));
-    const int32_t* base = static_cast<const int32_t*>(p->d_blob);
-    PlanDev& d = p->dev;
+    void* blob = nullptr;
+    BFE2_CUDA(cudaMalloc(&blob, bytes));
+    if (cudaMemcpy(blob, host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(blob);
+        return fail(-100, "plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    const int32_t* base = static_cast<const int32_t*>(blob);
+    PlanDev d{};
     d.nN = p->nN; d.nE = p->nE; d.sumdof = p->sumdof; d.n = p->n; d.hbw = p->hbw; d.nslots = p->nslots;
     d.npad = p->npad; d.LD = p->LD; d.off = p->npad - p->n;
     d.conn = base + off[0];
@@ -173,19 +172,15 @@ int plan_upload(bfe2_plan* p) {
     d.contrib_k = base + off[7];
     d.contrib_m = base + off[8];
     d.lumped = reinterpret_cast<const uint8_t*>(base + off[NA]);
-    p->uploaded = true;
-    p->device = dev;
-    p->copies[dev] = std::make_pair(p->d_blob, p->dev);
+    p->copies[dev] = std::make_pair(blob, d);
+    *out = d;
     return 0;
 }
 
 }  // namespace
 
-// shared with bfe2_post.cu: device view of a plan (uploads lazily); NULL + last_error on failure
-const PlanDev* bfe2_plan_device_view(bfe2_plan* plan) {
-    if (plan_upload(plan) != 0) return nullptr;
-    return &plan->dev;
-}
+// shared with bfe2_post.cu: device view of a plan on the current device (uploads lazily); < 0 + last_error on failure
+int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out) { return plan_upload(plan, out); }
 
 // =================================================================================================
 // kernels
@@ -689,7 +684,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
 }
 
 template <int G, int HB, bool ASSEMBLE>
-int launch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+int launch_static_group(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const GroupLayout GL = group_layout(plan->nE, plan->n, plan->nslots, A.C, G);
     const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1 + plan->nslots + 1 +
                                   plan->ncontrib) * sizeof(int) + 16;
@@ -714,18 +709,18 @@ int launch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream
     const long long per_block = (long long)nw * (32 / G);
     const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
     const int grid = (int)std::min<long long>((A.B + per_block - 1) / per_block, (long long)sms * resident);
-    kern<<<grid, nw * 32, bytes, stream>>>(plan->dev, A, plan->ncontrib);
+    kern<<<grid, nw * 32, bytes, stream>>>(pd, A, plan->ncontrib);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
 
 // 0: launched; 1: this plan does not fit the group kernel (wide band / too much shared memory); < 0: error
 template <bool ASSEMBLE>
-int dispatch_static_group(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+int dispatch_static_group(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     // 16 lanes per structure: measured best of 4 / 8 / 16 / 32 (profiles/r1_ablation.md)
     if (plan->hbw > 8 || plan->nE == 0) return 1;
-    return plan->hbw <= 5 ? launch_static_group<16, 5, ASSEMBLE>(plan, A, stream)
-                          : launch_static_group<16, 8, ASSEMBLE>(plan, A, stream);
+    return plan->hbw <= 5 ? launch_static_group<16, 5, ASSEMBLE>(plan, pd, A, stream)
+                          : launch_static_group<16, 8, ASSEMBLE>(plan, pd, A, stream);
 }
 
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
@@ -881,9 +876,9 @@ k_solve(PlanDev P, BatchArgs A) {
 }
 
 template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
-int launch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
-    PlanDev P = plan->dev;
+    PlanDev P = pd;
     P.off = REGS ? 0 : plan->npad - plan->n;
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
@@ -896,17 +891,17 @@ int launch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
 }
 
 template <bool ASSEMBLE>
-int dispatch_solve(bfe2_plan* plan, const BatchArgs& A, cudaStream_t stream) {
+int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     // n <= 58: register-resident, preconditioned odd-even Jacobi (two warps per structure);
     // 58 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
     if (plan->lpp == 2) {
-        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
-        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, A, stream);
+        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
+        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
         // __launch_bounds__(64, 5): same 168 registers and 6 resident blocks as (64, 6), but ptxas schedules the
         // software-pipelined step better (+4.7 % measured); (64, 4) takes 216 registers, 4 blocks and is slower.
-        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, A, stream);
+        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
     }
-    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
 
@@ -1117,7 +1112,8 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
                          const double* nodal_mass, double* Kb, double* Mb, void* stream) {
     if (plan && B == 0) return 0;
     if (!plan || B < 0 || !coords || !props || !Kb) return fail(-1, "bfe2_assemble_banded: bad argument");
-    if (int r = plan_upload(plan)) return r;
+    PlanDev pd;
+    if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
     const size_t per_warp = (size_t)(20 * plan->nE) * sizeof(double);
@@ -1133,7 +1129,7 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
     const long long want = (B + nw - 1) / nw;
     const int grid = (int)std::min<long long>(want, (long long)sms * resident);
-    k_assemble<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(plan->dev, A, plan->ncontrib);
+    k_assemble<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(pd, A, plan->ncontrib);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1144,12 +1140,13 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     if (plan && B == 0) return 0;
     if (!plan || B < 0 || C < 1 || !Kb || !coords || !props || !f_nodal || !u || !info)
         return fail(-1, "bfe2_static_solve: bad argument");
-    if (int r = plan_upload(plan)) return r;
+    PlanDev pd;
+    if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.C = C; A.do_static = 1; A.do_modal = 0; A.max_sweeps = BFE2_MAX_SWEEPS;
     A.coords = coords; A.props = props; A.f_nodal = f_nodal; A.r_local = r_local; A.Kb_in = Kb;
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.info = info;
-    if (const int r = dispatch_static_group<false>(plan, A, (cudaStream_t)stream); r <= 0) return r;
+    if (const int r = dispatch_static_group<false>(plan, pd, A, (cudaStream_t)stream); r <= 0) return r;
     const size_t per_warp = (size_t)(((2 * plan->nN + 4 * plan->nE + 3 * plan->nE + plan->nslots + plan->n +
                                        C * (plan->n + 3 * plan->nN + 6 * plan->nE)) + 1) & ~1) * sizeof(double);
     const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1) * sizeof(int) + 16;
@@ -1164,7 +1161,7 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
     const long long want = (B + nw - 1) / nw;
     const int grid = (int)std::min<long long>(want, (long long)sms * resident);
-    k_static_warp<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(plan->dev, A);
+    k_static_warp<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(pd, A);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1176,11 +1173,12 @@ int bfe2_modal_solve(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* 
     if (n_modes < 0 || n_modes > plan->n || (n_modes > 0 && !phi)) return fail(-1, "bad n_modes");
     if (plan->rpl == 0) return fail(-3, "n_free = %d is outside the Jacobi path (1..%d)", plan->n, BFE2_MAX_JACOBI_N);
     if (B == 0) return 0;
-    if (int r = plan_upload(plan)) return r;
+    PlanDev pd;
+    if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.C = 0; A.do_static = 0; A.do_modal = 1; A.n_modes = n_modes; A.max_sweeps = BFE2_MAX_SWEEPS;
     A.Kb_in = Kb; A.Mb_in = Mb; A.lam = lam; A.phi = phi; A.info = info; A.sweeps = sweeps;
-    return dispatch_solve<false>(plan, A, (cudaStream_t)stream);
+    return dispatch_solve<false>(plan, pd, A, (cudaStream_t)stream);
 }
 
 int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, int32_t n_modes,
@@ -1199,7 +1197,8 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
             return fail(-3, "n_free = %d is outside the Jacobi path (1..%d)", plan->n, BFE2_MAX_JACOBI_N);
     }
     if (B == 0) return 0;
-    if (int r = plan_upload(plan)) return r;
+    PlanDev pd;
+    if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.C = C; A.do_static = C > 0; A.do_modal = do_modal != 0; A.n_modes = do_modal ? n_modes : 0;
     A.max_sweeps = BFE2_MAX_SWEEPS;
@@ -1207,8 +1206,8 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.lam = lam; A.phi = phi;
     A.info = info; A.sweeps = sweeps;
     if (!do_modal) {
-        if (const int r = dispatch_static_group<true>(plan, A, (cudaStream_t)stream); r <= 0) return r;
-        PlanDev P = plan->dev;
+        if (const int r = dispatch_static_group<true>(plan, pd, A, (cudaStream_t)stream); r <= 0) return r;
+        PlanDev P = pd;
         P.npad = 0; P.LD = 0;
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
         const size_t bytes = (size_t)L.total * sizeof(double);
@@ -1220,7 +1219,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         BFE2_CUDA(cudaGetLastError());
         return 0;
     }
-    return dispatch_solve<true>(plan, A, (cudaStream_t)stream);
+    return dispatch_solve<true>(plan, pd, A, (cudaStream_t)stream);
 }
 
 

@@ -15,7 +15,7 @@
 using namespace bfe2;
 
 int bfe2_fail(int code, const char* fmt, ...);
-const PlanDev* bfe2_plan_device_view(bfe2_plan* plan);   // bfe2.cu: uploads if needed, NULL on error
+int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out);   // bfe2.cu: view on the current device, < 0 on error
 
 namespace {
 
@@ -88,8 +88,9 @@ int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, c
     if (plan && B == 0) return 0;
     if (!plan || B < 0 || C < 1 || npts < 1 || !coords || !endforces || (!actions && !maxabs))
         return bfe2_fail(-1, "bfe2_internal_actions: bad argument");
-    const PlanDev* P = bfe2_plan_device_view(plan);
-    if (!P) return -100;
+    PlanDev pd;
+    if (const int r = bfe2_plan_device_view(plan, &pd)) return r;
+    const PlanDev* P = &pd;
     const long long total = B * C * P->nE;
     k_internal_actions<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, B, C, npts, coords, endforces,
                                                                                            q_axial, q_perp, actions, maxabs);
@@ -101,8 +102,9 @@ int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const 
                              double* gamma, void* stream) {
     if (plan && B == 0) return 0;
     if (!plan || B < 0 || n_modes < 1 || !Mb || !phi || !gamma) return bfe2_fail(-1, "bfe2_modal_participation: bad argument");
-    const PlanDev* P = bfe2_plan_device_view(plan);
-    if (!P) return -100;
+    PlanDev pd;
+    if (const int r = bfe2_plan_device_view(plan, &pd)) return r;
+    const PlanDev* P = &pd;
     const long long total = B * n_modes;
     k_participation<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, B, n_modes, Mb, phi, gamma);
     if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_participation launch failed");

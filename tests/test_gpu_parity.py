@@ -434,3 +434,37 @@ def test_one_plan_on_two_devices():
     ref = outs[0]
     for o in outs[1:]:
         assert torch.equal(o['lam'].cpu(), ref['lam'].cpu()) and torch.equal(o['u'].cpu(), ref['u'].cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_one_plan_from_two_host_threads():
+    """One plan, one host thread per GPU, concurrent launches (ctypes drops the GIL): every call must get the plan
+    copy of ITS device -- the plan keeps no 'current device' state."""
+    import threading
+    conn, sup = sweep.p20_topology()
+    plan = Plan.from_supports(21, conn, sup)                    # first upload happens inside the threads
+    P = sweep.p20_draw_params(256)
+    results, errors = {}, []
+
+    def work(d):
+        try:
+            with torch.cuda.device(d):
+                pk = sweep.p20_pack(torch.from_numpy(P).to('cuda:%d' % d))
+                outs = [batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'],
+                                          pk['r_local'], n_modes=4) for _ in range(20)]
+                torch.cuda.synchronize(d)
+                results[d] = [(o['lam'].cpu(), o['u'].cpu(), o['info'].cpu()) for o in outs]
+        except Exception as e:                                      # noqa: BLE001
+            errors.append((d, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    ref = results[0][0]
+    for d in (0, 1):
+        for lam, u, info in results[d]:
+            assert int(info.abs().sum()) == 0
+            assert torch.equal(lam, ref[0]) and torch.equal(u, ref[1])
