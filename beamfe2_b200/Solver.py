@@ -17,6 +17,10 @@ class Solver(object):
         raise NotImplementedError
 
 
+MAX_JACOBI_N = 116        # BFE2_MAX_JACOBI_N (include/bfe2.h): largest n_free of the batched all-modes path
+LARGE_N_MODES = 40        # modes returned for larger structures (first-k route)
+
+
 def _run(structure, static, modal):
     import torch
     from . import batch
@@ -60,6 +64,8 @@ class ModalSolver(Solver):
             return False
         if np.count_nonzero(pk['props'][:, 3] * pk['props'][:, 1]) == 0 and np.count_nonzero(pk['nodal_mass']) == 0:
             return False                                                        # all-zero mass, Solver.py:34-35
+        if plan.n_free > MAX_JACOBI_N:
+            return self._solve_large(plan, pk)
         plan, out = _run(st, static=False, modal=True)
         info = int(out['info'])
         if info == -1:
@@ -69,6 +75,31 @@ class ModalSolver(Solver):
         lam = out['lam']
         circfreq = [math.sqrt(x) for x in lam if x > 0]                         # Solver.py:42
         shapes = [np.matrix(out['phi'][k]).T for k in range(out['phi'].shape[0])]
+        st.results['modal'] = Results.ModalResult(structure=st, circular_freq=circfreq, modalshapes=shapes)
+        st.results['modal'].solved = True
+        return True
+
+
+    def _solve_large(self, plan, pk):
+        """n_free beyond the batched Jacobi path: the lowest modes by subspace iteration (frame_modes.FrameModes).
+        The reference would return all n_free eigenpairs (dense LAPACK, Solver.py:39); this returns the first
+        `LARGE_N_MODES`."""
+        import torch
+        from .frame_modes import FrameModes
+        if not torch.cuda.is_available():
+            raise RuntimeError('beamfe2_b200 solvers need a CUDA device (no CPU fallback)')
+
+        def dev(a):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda')
+        fm = FrameModes(plan, dev(pk['coords']), dev(pk['props']), dev(pk['nodal_mass']))
+        out = fm.modes(n_modes=LARGE_N_MODES)
+        if out.get('failed') or out['phi'] is None:
+            raise np.linalg.LinAlgError('modal solve failed (subspace iteration did not produce a Ritz basis)')
+        st = self.structure
+        lam = out['lam'].cpu().numpy()
+        phi = out['phi'].cpu().numpy()
+        circfreq = [math.sqrt(x) for x in lam if x > 0]
+        shapes = [np.matrix(phi[k]).T for k in range(phi.shape[0])]
         st.results['modal'] = Results.ModalResult(structure=st, circular_freq=circfreq, modalshapes=shapes)
         st.results['modal'].solved = True
         return True

@@ -23,60 +23,22 @@ def _sp():
     return torch.cuda.current_stream().cuda_stream
 
 
-class LargeBeam:
-    """coords [nN, 2], props [nE, 4] (E, A, I, rho): CUDA float64; nodes numbered along the chain (beam k joins
-    nodes k and k+1); fixed_positions = Structure.positions_to_eliminate (global DOF positions)."""
+class SubspaceIteration:
+    """Shift-invert (sigma = 0) subspace iteration with a block of 64 vectors.  A subclass provides the operator:
+    `n`, `device`, `fixed_mask` (uint8 [n], 1 = DOF held at zero), `solve(F, out=None)` = K^-1 F and
+    `matvec(X, mass, out=None)` = K X or M X for F, X [n, 64]."""
 
-    def __init__(self, coords, props, fixed_positions, n_partitions: int = 0):
-        L = _lib.lib()
-        assert coords.is_cuda and props.is_cuda and coords.dtype == torch.float64 and props.dtype == torch.float64
-        self.coords, self.props = coords.contiguous(), props.contiguous()
-        nE = props.shape[0]
-        assert coords.shape == (nE + 1, 2) and props.shape == (nE, 4)
-        self.n_elem, self.n_nodes, self.n = nE, nE + 1, 3 * (nE + 1)
-        mask = np.zeros(self.n, dtype=np.uint8)
-        mask[np.asarray(list(fixed_positions), dtype=np.int64)] = 1
-        self.fixed_mask = mask
-        self.device = coords.device
-        h = C.c_void_p()
-        with torch.cuda.device(self.device):
-            _lib.check(L.bfe2_beam_create(C.byref(h), nE, _lib.ptr(self.coords), _lib.ptr(self.props), _lib.ptr(mask),
-                                          int(n_partitions), _sp()))
-        self._h = h
-        nn, nd, npart = C.c_int64(), C.c_int64(), C.c_int32()
-        _lib.check(L.bfe2_beam_dims(h, C.byref(nn), C.byref(nd), C.byref(npart)))
-        self.n_partitions = npart.value
-        self._dense_plan = None
-        self._gram_ws = None
+    _dense_plan = None
+    _gram_ws = None
+    _eig_ws = None
 
-    def __del__(self):
+    def _free_small(self):
         try:
-            if getattr(self, '_h', None):
-                _lib.lib().bfe2_beam_destroy(self._h)
-                self._h = None
             if getattr(self, '_dense_plan', None):
                 _lib.lib().bfe2_plan_destroy(self._dense_plan)
                 self._dense_plan = None
         except Exception:
             pass
-
-    # ---- building blocks ---------------------------------------------------------------------
-    def solve(self, F, out=None):
-        """U = K^-1 F for F [n, nrhs] (or [n])."""
-        vec = F.dim() == 1
-        F2 = F.reshape(self.n, -1).contiguous()
-        U = torch.empty_like(F2) if out is None else out
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().bfe2_beam_solve(self._h, F2.shape[1], _lib.ptr(F2), _lib.ptr(U), _sp()))
-        return U.reshape(self.n) if vec else U
-
-    def matvec(self, X, mass=False, out=None):
-        vec = X.dim() == 1
-        X2 = X.reshape(self.n, -1).contiguous()
-        Y = torch.empty_like(X2) if out is None else out
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().bfe2_beam_matvec(self._h, 1 if mass else 0, X2.shape[1], _lib.ptr(X2), _lib.ptr(Y), _sp()))
-        return Y.reshape(self.n) if vec else Y
 
     def gram(self, X, Y):
         """X^T Y on the FP64 tensor cores, X, Y [n, 64]."""
@@ -145,14 +107,6 @@ class LargeBeam:
         Qm = (d[:, None] * P.t()) * torch.rsqrt(mu_c)[None, :]          # q_j = D p_j / sqrt(mu_j)
         return theta, Qm.contiguous(), info
 
-    # ---- analyses ----------------------------------------------------------------------------
-    def static(self, f):
-        """Displacements for the load vector(s) f [n] or [n, C]; supported DOFs are forced to zero load."""
-        f = f.clone()
-        fm = torch.as_tensor(self.fixed_mask.astype(bool), device=self.device)
-        f[fm] = 0.0
-        return self.solve(f)
-
     def modal(self, n_modes=50, tol=1e-10, maxit=80, seed=0, verbose=False):
         """Lowest n_modes (<= 56) eigenpairs by subspace iteration.  Returns dict(lam [n_modes],
         phi [n_modes, n] M-normalised, iterations, residual [n_modes] = ||K phi - lam M phi||_inf /
@@ -213,3 +167,65 @@ class LargeBeam:
         res = R.abs().amax(dim=0) / (max(kmax, 1e-300) * Phi.abs().amax(dim=0))
         return dict(lam=lam, phi=Phi.t().contiguous(), iterations=it, residual=res, converged=conv,
                     noise_floor=None if conv else best, failed=failed)
+
+
+class LargeBeam(SubspaceIteration):
+    """coords [nN, 2], props [nE, 4] (E, A, I, rho): CUDA float64; nodes numbered along the chain (beam k joins
+    nodes k and k+1); fixed_positions = Structure.positions_to_eliminate (global DOF positions)."""
+
+    def __init__(self, coords, props, fixed_positions, n_partitions: int = 0):
+        L = _lib.lib()
+        assert coords.is_cuda and props.is_cuda and coords.dtype == torch.float64 and props.dtype == torch.float64
+        self.coords, self.props = coords.contiguous(), props.contiguous()
+        nE = props.shape[0]
+        assert coords.shape == (nE + 1, 2) and props.shape == (nE, 4)
+        self.n_elem, self.n_nodes, self.n = nE, nE + 1, 3 * (nE + 1)
+        mask = np.zeros(self.n, dtype=np.uint8)
+        mask[np.asarray(list(fixed_positions), dtype=np.int64)] = 1
+        self.fixed_mask = mask
+        self.device = coords.device
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.bfe2_beam_create(C.byref(h), nE, _lib.ptr(self.coords), _lib.ptr(self.props), _lib.ptr(mask),
+                                          int(n_partitions), _sp()))
+        self._h = h
+        nn, nd, npart = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(L.bfe2_beam_dims(h, C.byref(nn), C.byref(nd), C.byref(npart)))
+        self.n_partitions = npart.value
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.lib().bfe2_beam_destroy(self._h)
+                self._h = None
+            if getattr(self, '_dense_plan', None):
+                _lib.lib().bfe2_plan_destroy(self._dense_plan)
+                self._dense_plan = None
+        except Exception:
+            pass
+
+    # ---- building blocks ---------------------------------------------------------------------
+    def solve(self, F, out=None):
+        """U = K^-1 F for F [n, nrhs] (or [n])."""
+        vec = F.dim() == 1
+        F2 = F.reshape(self.n, -1).contiguous()
+        U = torch.empty_like(F2) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bfe2_beam_solve(self._h, F2.shape[1], _lib.ptr(F2), _lib.ptr(U), _sp()))
+        return U.reshape(self.n) if vec else U
+
+    def matvec(self, X, mass=False, out=None):
+        vec = X.dim() == 1
+        X2 = X.reshape(self.n, -1).contiguous()
+        Y = torch.empty_like(X2) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bfe2_beam_matvec(self._h, 1 if mass else 0, X2.shape[1], _lib.ptr(X2), _lib.ptr(Y), _sp()))
+        return Y.reshape(self.n) if vec else Y
+
+    # ---- analyses ----------------------------------------------------------------------------
+    def static(self, f):
+        """Displacements for the load vector(s) f [n] or [n, C]; supported DOFs are forced to zero load."""
+        f = f.clone()
+        fm = torch.as_tensor(self.fixed_mask.astype(bool), device=self.device)
+        f[fm] = 0.0
+        return self.solve(f)

@@ -117,3 +117,70 @@ def test_random_frame_static_and_modal(n_nodes, extra, n_cl, n_pin, reorder):
     gap = np.minimum(np.diff(o['lam'], axis=1, prepend=-np.inf), np.diff(o['lam'], axis=1, append=np.inf))[:, :phi.shape[1]]
     tol_v = 1e-10 + 256 * EPS * o['lam'][:, -1:] / gap
     assert (util.mode_err(phi, o['phi']) < tol_v).all()
+
+
+def test_first_modes_of_a_frame_beyond_the_jacobi_path():
+    """A 3-storey, 5-bay frame with 2 elements per member (n_free = 189 > 116): the lowest modes by subspace
+    iteration (frame_modes.FrameModes) against scipy.linalg.eigh on the oracle's dense K, M; and the drop-in
+    ModalSolver taking that route."""
+    import scipy.linalg as sla
+    from beamfe2_b200.frame_modes import FrameModes
+
+    def T(a):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+    from beamfe2_b200 import HermitianBeam_2D as HB, Node, Structure
+    storeys, bays, H, Lb = 3, 5, 3000.0, 5000.0
+    nodes, idx = [], {}
+
+    def node(x, y):
+        key = (round(x, 6), round(y, 6))
+        if key not in idx:
+            idx[key] = len(nodes)
+            nodes.append((x, y))
+        return idx[key]
+
+    conn, kinds = [], []
+    for b in range(bays + 1):                                    # columns, two elements per storey
+        for s_ in range(storeys):
+            ys = [s_ * H, s_ * H + H / 2, (s_ + 1) * H]
+            for a, c in zip(ys[:-1], ys[1:]):
+                conn.append((node(b * Lb, a), node(b * Lb, c)))
+                kinds.append(0)
+    for s_ in range(1, storeys + 1):                             # girders, two elements per bay
+        for b in range(bays):
+            xs = [b * Lb, b * Lb + Lb / 2, (b + 1) * Lb]
+            for a, c in zip(xs[:-1], xs[1:]):
+                conn.append((node(a, s_ * H), node(c, s_ * H)))
+                kinds.append(1)
+    xy = np.array(nodes)
+    conn = np.array(conn, dtype=np.int32)
+    props = np.array([[2.1e5, 300.0 * 300.0, 300.0 ** 4 / 12, 7.85e-9] if k == 0 else
+                      [2.1e5, 200.0 * 500.0, 200.0 * 500.0 ** 3 / 12, 7.85e-9] for k in kinds])
+    fixed = sorted(3 * i + d for i, (x, y) in enumerate(nodes) if y == 0.0 for d in range(3))
+    plan = Plan(len(nodes), conn, fixed, reorder=True)
+    assert plan.n_free > 116
+    mass = np.zeros((len(nodes), 2))
+    mass[[i for i, (x, y) in enumerate(nodes) if y > 0 and abs(y / H - round(y / H)) < 1e-9], :] = 2.0
+    fm = FrameModes(plan, T(xy), T(props), T(mass))
+    out = fm.modes(n_modes=20)
+    assert out['converged']
+    o = orc.solve_batch(conn, fixed, xy, props, nodal_mass=mass)
+    w = sla.eigh(o['Kc'], o['Mc'], eigvals_only=True)
+    lam = out['lam'].cpu().numpy()
+    assert np.abs(lam / w[:20] - 1).max() < 1e-8
+    keep = np.setdiff1d(np.arange(plan.sumdof), fixed)           # the oracle's condensed (ascending) numbering
+    phi = out['phi'].cpu().numpy()[:, keep]
+    assert np.abs(phi @ o['Mc'] @ phi.T - np.eye(20)).max() < 1e-8
+    assert float(out['residual'].max().item()) < 1e-9
+    # drop-in route
+    ns = [Node.Node(ID=i + 1, coords=tuple(p)) for i, p in enumerate(nodes)]
+    beams = [HB.HermitianBeam2D(ID=e + 1, E=props[e, 0], A=props[e, 1], I=props[e, 2], rho=props[e, 3],
+                                i=ns[conn[e, 0]], j=ns[conn[e, 1]]) for e in range(len(conn))]
+    sup = {i + 1: ['ux', 'uy', 'rotz'] for i, (x, y) in enumerate(nodes) if y == 0.0}
+    st = Structure.Structure(beams=beams, supports=sup)
+    for i, (x, y) in enumerate(nodes):
+        if mass[i, 0] > 0:
+            st.add_nodal_mass(nodeID=i + 1, mass={'mx': 2.0, 'my': 2.0})
+    assert st.solver['modal'].solve()
+    om = np.array(st.results['modal'].circular_frequencies[:20])
+    assert np.abs(om / np.sqrt(w[:20]) - 1).max() < 1e-8
