@@ -184,3 +184,75 @@ def test_first_modes_of_a_frame_beyond_the_jacobi_path():
     assert st.solver['modal'].solve()
     om = np.array(st.results['modal'].circular_frequencies[:20])
     assert np.abs(om / np.sqrt(w[:20]) - 1).max() < 1e-8
+
+
+@pytest.mark.parametrize('n_nodes,extra,C,B,reorder', [
+    (4, 0, 1, 1, False), (6, 1, 3, 3, True), (9, 2, 5, 45, True), (12, 3, 17, 7, True),
+    (16, 4, 2, 1000, True), (20, 0, 3, 33, True), (25, 6, 4, 5, False), (30, 3, 3, 129, True)])
+def test_static_only_kernels_on_general_frames(n_nodes, extra, C, B, reorder):
+    """The static-only entry points (fused from coordinates, and K2 -> K3 from the band in HBM) on general
+    frames: narrow bands run the 16-lanes-per-structure kernel (5- and 8-wide instantiations, with and without
+    the early right-hand-side path, more load cases than lanes), wide bands the block / warp fallbacks; ragged
+    batch sizes; optional outputs."""
+    rng = np.random.default_rng(77 * n_nodes + C)
+    xy, conn, fixed = random_frame(rng, n_nodes, extra, 1, 1)
+    _check_static_only(rng, xy, conn, fixed, C, B, reorder)
+
+
+@pytest.mark.parametrize('n_nodes,skip,C,B', [(3, 0, 1, 1), (8, 0, 3, 45), (21, 0, 3, 1000), (21, 0, 17, 7),
+                                              (12, 1, 1, 3), (20, 1, 3, 130), (15, 1, 20, 33), (40, 0, 2, 9)])
+def test_static_only_kernels_on_narrow_bands(n_nodes, skip, C, B):
+    """Chains (half bandwidth 5) and chains with extra beams from node k to k + 2 (half bandwidth 8): the two
+    instantiations of the 16-lanes-per-structure kernel, 1 .. 20 load cases, ragged batches."""
+    rng = np.random.default_rng(5 * n_nodes + C + skip)
+    xy = np.stack([np.arange(n_nodes) * 700.0, 300.0 * np.sin(np.arange(n_nodes))], axis=1)
+    conn = [(k, k + 1) for k in range(n_nodes - 1)]
+    if skip:
+        conn += [(k, k + 2) for k in range(0, n_nodes - 2, 2)]
+    conn = np.array(conn, dtype=np.int32)
+    fixed = [0, 1, 2] + ([3 * (n_nodes - 1) + 1] if n_nodes > 4 else [])
+    plan = Plan(n_nodes, conn, fixed)
+    assert plan.hbw == (8 if skip else 5)
+    _check_static_only(rng, xy, conn, fixed, C, B, False)
+
+
+def _check_static_only(rng, xy, conn, fixed, C, B, reorder):
+    n_nodes = len(xy)
+    nE = len(conn)
+    coords = xy[None] + rng.uniform(-20, 20, (B, n_nodes, 2))
+    props = np.stack([rng.uniform(1.9e5, 2.2e5, (B, nE)), rng.uniform(2e3, 2e4, (B, nE)),
+                      rng.uniform(1e6, 1e8, (B, nE)), rng.uniform(7e-9, 8.5e-9, (B, nE))], axis=-1)
+    f_nodal = rng.uniform(-1e4, 1e4, (B, C, 3 * n_nodes)) * (rng.uniform(size=(1, C, 3 * n_nodes)) < 0.3)
+    f_nodal[:, :, 0] += 1.0
+    L, _ = orc.length_direction(coords, conn)
+    q = rng.uniform(-5, 5, (B, C, nE)) * (rng.uniform(size=(1, C, nE)) < 0.5)
+    Lc = np.broadcast_to(L[:, None, :], q.shape)
+    r_local = np.zeros((B, C, nE, 6))
+    r_local[..., 1] = q * Lc / 2
+    r_local[..., 2] = q * (Lc ** 2) / 12
+    r_local[..., 4] = q * Lc / 2
+    r_local[..., 5] = -1 * q * (Lc ** 2) / 12.
+    plan = Plan(n_nodes, conn, fixed, None, reorder=reorder)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)     # noqa: E731
+    nb = min(B, 6)                                                     # oracle on the first and last few variants
+    pick = np.r_[0:nb // 2, B - (nb - nb // 2):B] if B > nb else np.arange(B)
+    o = orc.solve_batch(conn, fixed, coords[pick], props[pick], None, f_nodal[pick], r_local[pick])
+    condK = np.linalg.cond(o['K'][:, orc.free_positions(n_nodes, fixed)][:, :, orc.free_positions(n_nodes, fixed)]).max()
+    tol = max(1e-10, 50 * EPS * condK)
+    fused = batch.solve_fused(plan, T(coords), T(props), None, T(f_nodal), T(r_local), modal=False)
+    Kb, _ = batch.assemble_banded(plan, T(coords), T(props), None)
+    unfused = batch.static_solve(plan, Kb, T(coords), T(props), T(f_nodal), T(r_local))
+    for out in (fused, unfused):
+        assert (out['info'] == 0).all()
+        for k, b in enumerate(pick):
+            for key in ('u', 'endforces', 'reactions'):
+                assert util.relmax(out[key][b].cpu().numpy(), o[key][k]) < tol, (key, int(b))
+    # optional outputs and no beam loads: displacements do not depend on what else is requested
+    u_only = batch.solve_fused(plan, T(coords), T(props), None, T(f_nodal), T(r_local), modal=False,
+                               want_endforces=False, want_reactions=False)
+    assert torch.equal(u_only['u'], fused['u']) and u_only['endforces'] is None and u_only['reactions'] is None
+    o0 = orc.solve_batch(conn, fixed, coords[pick], props[pick], None, f_nodal[pick], np.zeros_like(r_local[pick]))
+    nob = batch.solve_fused(plan, T(coords), T(props), None, T(f_nodal), None, modal=False)
+    for k, b in enumerate(pick):
+        assert util.relmax(nob['u'][b].cpu().numpy(), o0['u'][k]) < tol
+        assert util.relmax(nob['reactions'][b].cpu().numpy(), o0['reactions'][k]) < tol
