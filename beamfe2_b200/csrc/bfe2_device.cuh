@@ -386,11 +386,13 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
     }
 }
 
-// The factorisation by the G lanes of a group (the warp's groups run it in lockstep, each on its own band):
-// per column, lanes 1..m scale the subdiagonal, then lane t takes the trailing-update pair (p, q) number t.
-// In place in shared memory; 1 / L[j][j] goes to invdiag, which holds the ORIGINAL diagonal until column j is
-// eliminated (the relative pivot test).  Returns 0 or the 1-based column of the first bad pivot, uniform per
-// group; a failed group keeps running in lockstep without storing.
+// The factorisation by the G lanes of a group (the warp's groups run it in lockstep, each on its own band).
+// Root-free elimination first: per column only the trailing update  A[j+p][j+q] -= A[j+p][j] A[j+q][j] / pivot
+// (lane t owns pair (p, q) number t) and ONE __syncwarp -- no scaled column has to be stored and re-read inside
+// the column loop; then one lane-parallel pass turns the unscaled columns into the Cholesky factor
+// (L[i][j] = A[i][j] / sqrt(pivot_j), invdiag[j] = 1 / L[j][j]).  invdiag holds the ORIGINAL diagonal until that
+// pass (the relative pivot test).  Returns 0 or the 1-based column of the first bad pivot, uniform per group; a
+// failed group keeps running in lockstep without storing.
 template <int G, int HB>
 __device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, int n, int b, int g) {
     for (int j = g; j < n; j += G) invdiag[j] = Ab[j];
@@ -413,20 +415,32 @@ __device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, 
         const int m = min(b, n - 1 - col);
         const double piv = Ab[col];
         const double orig = invdiag[col];
-        if (info == 0 && (!(piv > 1.4210854715202004e-14 * orig) || !isfinite(piv))) info = col + 1;
-        const double r = rsqrt_fast(piv);
-        if (info == 0)
-            for (int i = g; i <= m; i += G)
-                if (i > 0) Ab[i * n + col] *= r;
-        __syncwarp();
+        if (info == 0 && !(piv > 1.4210854715202004e-14 * orig && piv < INFINITY)) info = col + 1;
+        const double ip = rcp_fast(piv);
         if (info == 0) {
-            if (g == 0) { Ab[col] = piv * r; invdiag[col] = r; }
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k)
-                if (need[k] <= m) Ab[off_t[k] + col] = fma(-Ab[off_p[k] + col], Ab[off_q[k] + col], Ab[off_t[k] + col]);
+                if (need[k] <= m) {
+                    double* t = Ab + off_t[k] + col;
+                    *t = fma(-(Ab[off_p[k] + col] * ip), Ab[off_q[k] + col], *t);
+                }
         }
         __syncwarp();
     }
+    if (info == 0) {
+        for (int j = g; j < n; j += G) {
+            const double piv = Ab[j];
+            const double r = rsqrt_fast(piv);
+            invdiag[j] = r;
+            Ab[j] = piv * r;
+        }
+    }
+    __syncwarp();
+    if (info == 0) {
+        for (int d = 1; d <= b; ++d)
+            for (int j = g; j < n - d; j += G) Ab[d * n + j] *= invdiag[j];
+    }
+    __syncwarp();
     return info;
 }
 
