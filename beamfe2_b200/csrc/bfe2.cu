@@ -633,6 +633,12 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
             const int fj0 = c_fop[3 * nj], fj1 = c_fop[3 * nj + 1], fj2 = c_fop[3 * nj + 2];
             for (int c = 0; c < C; ++c) {
                 const double* x = s_a + c * n;
+                double rl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // in flight while Ke u_local is formed
+                if (have_r) {
+                    const double* r = g_r + (c * nE + e) * 6;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) rl[k] = r[k];
+                }
                 const double ui0 = fi0 >= 0 ? x[fi0] : 0.0, ui1 = fi1 >= 0 ? x[fi1] : 0.0, ui2 = fi2 >= 0 ? x[fi2] : 0.0;
                 const double uj0 = fj0 >= 0 ? x[fj0] : 0.0, uj1 = fj1 >= 0 ? x[fj1] : 0.0, uj2 = fj2 >= 0 ? x[fj2] : 0.0;
                 const double d0 = cs * ui0 + sn * ui1, d1 = cs * ui1 - sn * ui0;
@@ -645,11 +651,8 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
                 q[2] = fma(b6, d1 - d4, fma(b4, ui2, b2 * uj2));
                 q[5] = fma(b6, d1 - d4, fma(b2, ui2, b4 * uj2));
                 double* d = s_ef + (c * nE + e) * 6;
-                if (have_r) {
-                    const double* r = g_r + (c * nE + e) * 6;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) q[k] -= r[k];
-                }
+                for (int k = 0; k < 6; ++k) q[k] -= rl[k];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) d[k] = q[k];
                 if (g_ef != nullptr && valid) {
@@ -666,6 +669,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
             for (int c = 0; c < C; ++c)
                 for (int pos = g; pos < sumdof; pos += G) {
                     const int node = pos / 3, k = pos - 3 * node;
+                    const double fn = g_f[c * sumdof + pos];        // in flight while the end forces are summed
                     double v = 0.0;
                     for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
                         const int inc = c_ninc[q];
@@ -676,7 +680,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
                         else if (k == 1) v += sn * f[0] + cs * f[1];
                         else v += f[2];
                     }
-                    if (valid) g_re[c * sumdof + pos] = ok ? v - g_f[c * sumdof + pos] : qnan;
+                    if (valid) g_re[c * sumdof + pos] = ok ? v - fn : qnan;
                 }
         }
         __syncwarp();
