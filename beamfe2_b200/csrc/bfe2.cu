@@ -496,20 +496,22 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         }
         // 0. (fused path) this lane's right-hand-side entries go into registers and r_local into the band region,
         //    which is free until the assembly: every load of the right-hand sides is in flight before the first
-        //    use, instead of one dependent HBM round trip per incident beam.  Item k of a lane is the flat index
-        //    t = g + G k = c n + j.
-        constexpr int MAXI = 12;
-        const bool early_rhs = ASSEMBLE && have_r && (C * n + G - 1) / G <= MAXI && nr <= nslots + n;
-        double xr[MAXI];
+        //    use, instead of one dependent HBM round trip per incident beam.  Item k of a lane is the (load case,
+        //    node) pair number t = g + G k = c nN + node; it carries the three DOFs of the node.
+        constexpr int MAXI = 4;
+        const bool early_rhs = ASSEMBLE && have_r && (C * nN + G - 1) / G <= MAXI && nr <= nslots + n;
+        double xr[3 * MAXI];
         if (early_rhs) {
             for (int i = g; i < nr; i += G) cp_async8(s_Kb + i, g_r + i);
             cp_async_commit();
-            int c = 0, j = g;
+            int c = 0, node = g;
 #pragma unroll
             for (int k = 0; k < MAXI; ++k) {
-                while (j >= n) { j -= n; ++c; }
-                xr[k] = (c < C) ? g_f[c * sumdof + c_pof[j]] : 0.0;
-                j += G;
+                while (node >= nN) { node -= nN; ++c; }
+                const double* f3 = g_f + c * sumdof + 3 * node;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) xr[3 * k + d] = (c < C) ? f3[d] : 0.0;
+                node += G;
             }
         }
         // 1. beams: direction, 1/L, EA/L, EI/L and (fused path) the seven stiffness numbers
@@ -537,26 +539,22 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         if (early_rhs) {
             cp_async_wait<0>();
             __syncwarp();
-            int c = 0, j = g;
+            int c = 0, node = g;
 #pragma unroll
             for (int k = 0; k < MAXI; ++k) {
-                while (j >= n) { j -= n; ++c; }
+                while (node >= nN) { node -= nN; ++c; }
                 if (c < C) {
-                    const int pos = c_pof[j];
-                    const int node = pos / 3, dof = pos - 3 * node;
-                    double v = xr[k];
                     for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
                         const int inc = c_ninc[q];
                         const int e = inc >> 1;
                         const double* r = s_Kb + (c * nE + e) * 6 + 3 * (inc & 1);
                         const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
-                        if (dof == 0) v += cs * r[0] - sn * r[1];
-                        else if (dof == 1) v += sn * r[0] + cs * r[1];
-                        else v += r[2];
+                        xr[3 * k] += cs * r[0] - sn * r[1];
+                        xr[3 * k + 1] += sn * r[0] + cs * r[1];
+                        xr[3 * k + 2] += r[2];
                     }
-                    xr[k] = v;
                 }
-                j += G;
+                node += G;
             }
         }
         __syncwarp();
@@ -579,9 +577,19 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         const int info = band_cholesky_group<G, HB>(s_Kb, s_inv, n, hbw, g);
         // 4. right-hand sides in free numbering (over the stiffness numbers, which are dead now)
         if (early_rhs) {
+            int c = 0, node = g;
 #pragma unroll
-            for (int k = 0; k < MAXI; ++k)
-                if (g + G * k < C * n) s_a[g + G * k] = xr[k];
+            for (int k = 0; k < MAXI; ++k) {
+                while (node >= nN) { node -= nN; ++c; }
+                if (c < C) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int j = c_fop[3 * node + d];
+                        if (j >= 0) s_a[c * n + j] = xr[3 * k + d];
+                    }
+                }
+                node += G;
+            }
         }
         for (int c = 0; c < (early_rhs ? 0 : C); ++c) {
             for (int j = g; j < n; j += G) {
@@ -663,24 +671,30 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
             }
         }
         __syncwarp();
-        // 8. reactions per (load case, position)  (Results.py:92-127)
+        // 8. reactions per (load case, node): the rotated end forces of the incident beams minus the nodal loads
+        //    (Results.py:92-127)
         if (A.reactions != nullptr) {
             double* g_re = A.reactions + b * (long long)nf;
             for (int c = 0; c < C; ++c)
-                for (int pos = g; pos < sumdof; pos += G) {
-                    const int node = pos / 3, k = pos - 3 * node;
-                    const double fn = g_f[c * sumdof + pos];        // in flight while the end forces are summed
-                    double v = 0.0;
+                for (int node = g; node < nN; node += G) {
+                    const double* f3 = g_f + c * sumdof + 3 * node;
+                    const double fn0 = f3[0], fn1 = f3[1], fn2 = f3[2];     // in flight while the end forces are summed
+                    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
                     for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
                         const int inc = c_ninc[q];
                         const int e = inc >> 1;
                         const double* f = s_ef + (c * nE + e) * 6 + 3 * (inc & 1);
                         const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
-                        if (k == 0) v += cs * f[0] - sn * f[1];
-                        else if (k == 1) v += sn * f[0] + cs * f[1];
-                        else v += f[2];
+                        v0 += cs * f[0] - sn * f[1];
+                        v1 += sn * f[0] + cs * f[1];
+                        v2 += f[2];
                     }
-                    if (valid) g_re[c * sumdof + pos] = ok ? v - fn : qnan;
+                    if (valid) {
+                        double* o = g_re + c * sumdof + 3 * node;
+                        o[0] = ok ? v0 - fn0 : qnan;
+                        o[1] = ok ? v1 - fn1 : qnan;
+                        o[2] = ok ? v2 - fn2 : qnan;
+                    }
                 }
         }
         __syncwarp();
