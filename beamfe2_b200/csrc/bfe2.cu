@@ -592,22 +592,24 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
             }
         }
         for (int c = 0; c < (early_rhs ? 0 : C); ++c) {
-            for (int j = g; j < n; j += G) {
-                const int pos = c_pof[j];
-                double v = g_f[c * sumdof + pos];
+            for (int node = g; node < nN; node += G) {
+                const double* f3 = g_f + c * sumdof + 3 * node;
+                double v0 = f3[0], v1 = f3[1], v2 = f3[2];
                 if (have_r) {
-                    const int node = pos / 3, k = pos - 3 * node;
                     for (int q = c_nptr[node]; q < c_nptr[node + 1]; ++q) {
                         const int inc = c_ninc[q];
                         const int e = inc >> 1;
                         const double* r = g_r + (c * nE + e) * 6 + 3 * (inc & 1);
                         const double cs = s_geo[5 * e + 1], sn = s_geo[5 * e + 2];
-                        if (k == 0) v += cs * r[0] - sn * r[1];
-                        else if (k == 1) v += sn * r[0] + cs * r[1];
-                        else v += r[2];
+                        v0 += cs * r[0] - sn * r[1];
+                        v1 += sn * r[0] + cs * r[1];
+                        v2 += r[2];
                     }
                 }
-                s_a[c * n + j] = v;
+                const int j0 = c_fop[3 * node], j1 = c_fop[3 * node + 1], j2 = c_fop[3 * node + 2];
+                if (j0 >= 0) s_a[c * n + j0] = v0;
+                if (j1 >= 0) s_a[c * n + j1] = v1;
+                if (j2 >= 0) s_a[c * n + j2] = v2;
             }
         }
         __syncwarp();
