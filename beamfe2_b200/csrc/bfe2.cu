@@ -561,8 +561,20 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         // 2. band of K on the free DOFs
         if (ASSEMBLE) {
             for (int slot = g; slot < nslots; slot += G) {
+                const int q0 = c_sptr[slot], cnt = c_sptr[slot + 1] - q0;
+                // the first two contributions without a loop (a chain has one or two per slot), same beam order
                 double k = 0.0;
-                for (int q = c_sptr[slot]; q < c_sptr[slot + 1]; ++q) {
+                if (cnt > 0) {
+                    const int code = c_con[q0];
+                    const double v = s_a[code & 0x7fffffff];
+                    k = (code < 0) ? -v : v;
+                }
+                if (cnt > 1) {
+                    const int code = c_con[q0 + 1];
+                    const double v = s_a[code & 0x7fffffff];
+                    k += (code < 0) ? -v : v;
+                }
+                for (int q = q0 + 2; q < q0 + cnt; ++q) {
                     const int code = c_con[q];
                     const double v = s_a[code & 0x7fffffff];
                     k += (code < 0) ? -v : v;
