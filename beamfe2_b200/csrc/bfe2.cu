@@ -323,7 +323,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
         for (int slot = lane; slot < P.nslots; slot += 32) {
             const int p0 = c_ptr[slot], p1 = c_ptr[slot + 1];
             double k = 0.0, m = 0.0;
-            for (int p = p0; p < p1; ++p) {
+            auto add = [&](int p) {
                 const int ck = c_conk[p];
                 const double vk = w_k[ck & 0x7fffffff];
                 k += (ck < 0) ? -vk : vk;
@@ -332,7 +332,10 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
                     const double vm = w_m[cm & 0x7fffffff];
                     m += (cm < 0) ? -vm : vm;
                 }
-            }
+            };
+            if (p1 > p0) add(p0);                      // one or two contributions per slot on a chain: no loop
+            if (p1 > p0 + 1) add(p0 + 1);
+            for (int p = p0 + 2; p < p1; ++p) add(p);
             A.Kb_out[b * P.nslots + slot] = k;
             if (want_mass) {
                 if (slot < P.n && g_mass != nullptr) {
