@@ -423,11 +423,12 @@ k_static_warp(PlanDev P, BatchArgs A) {
 
 struct GroupLayout { int a, kb, per_group; };
 
-__host__ __device__ inline GroupLayout group_layout(int nE, int n, int nslots, int C, int G) {
+__host__ __device__ inline GroupLayout group_layout(int nE, int n, int band_w, int C, int G) {
     GroupLayout L;
+    const int nslots = band_w * n;                // column-major band: band_w doubles per column
     const int size_a = (8 * nE > C * n) ? 8 * nE : C * n;           // beam stiffness numbers | right-hand sides
     L.a = 5 * nE;                                 // after geo[nE][5] = 1/L, cos, sin, EA/L, EI/L
-    L.kb = L.a + size_a;                          // band [nslots] + 1/diag [n] | end forces [C][nE][6]
+    L.kb = (L.a + size_a + 1) & ~1;               // 16-byte aligned: band [W n] + original diagonal [n] | end forces [C][nE][6]
     int tot = L.kb + ((nslots + n > 6 * C * nE) ? nslots + n : 6 * C * nE);
     // group stride = G (mod 16 doubles): the groups of a half-warp tile the banks in the lane-parallel stages;
     // G >= 16: stride = 2 (mod 16) keeps lane 0 of the warp's groups apart in the lane-serial stages
@@ -453,7 +454,8 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, g = tid % G, gi = tid / G, ngb = blockDim.x / G;
     const int n = P.n, nE = P.nE, nN = P.nN, sumdof = P.sumdof, C = A.C, hbw = P.hbw, nslots = P.nslots;
-    const GroupLayout GL = group_layout(nE, n, nslots, C, G);
+    constexpr int W = BandCm<HB>::W;
+    const GroupLayout GL = group_layout(nE, n, W, C, G);
     // block-shared plan cache (contributions already decoded to beam*8 + value index, sign in bit 31)
     int* c_conn = reinterpret_cast<int*>(smem + (size_t)ngb * GL.per_group);
     int* c_fop = c_conn + 2 * nE;
@@ -473,8 +475,8 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
     __syncthreads();
     double* s_geo = smem + (size_t)gi * GL.per_group;            // [nE][5] = 1/L, cos, sin, EA/L, EI/L
     double* s_a = s_geo + GL.a;                                   // beam stiffness numbers, then right-hand sides
-    double* s_Kb = s_geo + GL.kb;
-    double* s_inv = s_Kb + nslots;
+    double* s_Kb = s_geo + GL.kb;                                 // column-major: s_Kb[j * W + d] = K[j + d][j]
+    double* s_inv = s_Kb + W * n;                                 // original diagonal during the factorisation
     double* s_ef = s_Kb;                                          // the band is dead once u is known
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const long long per_pass = (long long)gridDim.x * ngb;
@@ -494,7 +496,8 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         const double* p_pr = A.props + b * 4 * nE;
         if (!ASSEMBLE) {                                          // unfused K3: the band comes from HBM
             const double* g_Kb = A.Kb_in + b * nslots;
-            for (int slot = g; slot < nslots; slot += G) cp_async8(s_Kb + slot, g_Kb + slot);
+            for (int d = 0; d <= hbw; ++d)
+                for (int j = g; j < n; j += G) cp_async8(s_Kb + j * W + d, g_Kb + d * n + j);
             cp_async_commit();
         }
         // 0. (fused path) this lane's right-hand-side entries go into registers and r_local into the band region,
@@ -502,7 +505,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         //    use, instead of one dependent HBM round trip per incident beam.  Item k of a lane is the (load case,
         //    node) pair number t = g + G k = c nN + node; it carries the three DOFs of the node.
         constexpr int MAXI = 4;
-        const bool early_rhs = ASSEMBLE && have_r && (C * nN + G - 1) / G <= MAXI && nr <= nslots + n;
+        const bool early_rhs = ASSEMBLE && have_r && (C * nN + G - 1) / G <= MAXI && nr <= W * n + n;
         double xr[3 * MAXI];
         if (early_rhs) {
             for (int i = g; i < nr; i += G) cp_async8(s_Kb + i, g_r + i);
@@ -563,7 +566,9 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         __syncwarp();
         // 2. band of K on the free DOFs
         if (ASSEMBLE) {
-            for (int slot = g; slot < nslots; slot += G) {
+            for (int d = 0; d <= hbw; ++d)
+            for (int j = g; j < n; j += G) {
+                const int slot = d * n + j;
                 const int q0 = c_sptr[slot], cnt = c_sptr[slot + 1] - q0;
                 // the first two contributions without a loop (a chain has one or two per slot), same beam order
                 double k = 0.0;
@@ -582,14 +587,16 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
                     const double v = s_a[code & 0x7fffffff];
                     k += (code < 0) ? -v : v;
                 }
-                s_Kb[slot] = k;
+                s_Kb[j * W + d] = k;
             }
         } else {
             cp_async_wait<0>();
         }
+        for (int d = hbw + 1; d < W; ++d)                         // beyond the band (narrower than HB, padding)
+            for (int j = g; j < n; j += G) s_Kb[j * W + d] = 0.0;
         __syncwarp();
         // 3. factor: lane 0 of each group
-        const int info = band_cholesky_group<G, HB>(s_Kb, s_inv, n, hbw, g);
+        const int info = band_cholesky_group_cm<G, HB>(s_Kb, s_inv, n, g);
         // 4. right-hand sides in free numbering (over the stiffness numbers, which are dead now)
         if (early_rhs) {
             int c = 0, node = g;
@@ -629,10 +636,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
         }
         __syncwarp();
         // 5. substitute: one lane per load case
-        for (int c = g; c < C; c += G) {
-            if (hbw == HB) band_subst_exact<HB>(s_Kb, s_inv, s_a + c * n, n);
-            else band_subst_thread<HB, true, true>(s_Kb, s_inv, s_a + c * n, 1, n, hbw);
-        }
+        for (int c = g; c < C; c += G) band_subst_cm<HB>(s_Kb, s_a + c * n, n);
         __syncwarp();
         const bool ok = info == 0;
         if (valid && g == 0) A.info[b] = info;
@@ -720,7 +724,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
 
 template <int G, int HB, bool ASSEMBLE>
 int launch_static_group(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
-    const GroupLayout GL = group_layout(plan->nE, plan->n, plan->nslots, A.C, G);
+    const GroupLayout GL = group_layout(plan->nE, plan->n, BandCm<HB>::W, A.C, G);
     const size_t cache = (size_t)(4 * plan->nE + plan->sumdof + plan->n + plan->nN + 1 + plan->nslots + 1 +
                                   plan->ncontrib) * sizeof(int) + 16;
     const size_t per_warp = (size_t)(32 / G) * GL.per_group * sizeof(double);

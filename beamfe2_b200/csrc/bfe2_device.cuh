@@ -386,16 +386,20 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
     }
 }
 
-// The factorisation by the G lanes of a group (the warp's groups run it in lockstep, each on its own band).
-// Root-free elimination first: per column only the trailing update  A[j+p][j+q] -= A[j+p][j] A[j+q][j] / pivot
-// (lane t owns pair (p, q) number t) and ONE __syncwarp -- no scaled column has to be stored and re-read inside
-// the column loop; then one lane-parallel pass turns the unscaled columns into the Cholesky factor
-// (L[i][j] = A[i][j] / sqrt(pivot_j), invdiag[j] = 1 / L[j][j]).  invdiag holds the ORIGINAL diagonal until that
-// pass (the relative pivot test).  Returns 0 or the 1-based column of the first bad pivot, uniform per group; a
-// failed group keeps running in lockstep without storing.
+// ---- column-major band for the group kernel: column j is W = HB + 1 (rounded up to even) consecutive doubles
+//      Cc[j * W + d] = A[j + d][j], 16-byte aligned, entries outside the band or the matrix are zero.  After the
+//      factorisation slot d = 0 holds 1 / L[j][j] and d >= 1 holds L[j + d][j]: one substitution row is W / 2
+//      16-byte loads (all lanes of a group read the same column: broadcasts).
+template <int HB>
+struct BandCm { static constexpr int W = (HB + 2) & ~1; };
+
+// Root-free elimination by the G lanes of a group (lane t owns trailing-update pair (p, q) number t), one
+// __syncwarp per column, then one lane-per-column pass that scales the column and leaves 1 / L[j][j] in slot 0.
+// orig[j] receives the original diagonal (relative pivot test).  Returns 0 or the 1-based bad column.
 template <int G, int HB>
-__device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, int n, int b, int g) {
-    for (int j = g; j < n; j += G) invdiag[j] = Ab[j];
+__device__ __forceinline__ int band_cholesky_group_cm(double* Cc, double* orig, int n, int g) {
+    constexpr int W = BandCm<HB>::W;
+    for (int j = g; j < n; j += G) orig[j] = Cc[j * W];
     constexpr int NP = HB * (HB + 1) / 2, ROUNDS = (NP + G - 1) / G;
     int off_t[ROUNDS], off_p[ROUNDS], off_q[ROUNDS], need[ROUNDS];
 #pragma unroll
@@ -405,74 +409,81 @@ __device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, 
         while (p * (p + 1) / 2 <= t) ++p;            // t = p (p - 1) / 2 + (q - 1), 1 <= q <= p
         const int q = t - p * (p - 1) / 2 + 1;
         need[k] = (t < NP) ? p : HB + 1;             // the pair exists in a column with m >= p
-        off_p[k] = p * n;
-        off_q[k] = q * n;
-        off_t[k] = (p - q) * n + q;
+        off_p[k] = p;
+        off_q[k] = q;
+        off_t[k] = q * W + (p - q);                  // A[j+p][j+q] = Cc[(j+q) W + (p-q)]
     }
     __syncwarp();
     int info = 0;
     for (int col = 0; col < n; ++col) {
-        const int m = min(b, n - 1 - col);
-        const double piv = Ab[col];
-        const double orig = invdiag[col];
-        if (info == 0 && !(piv > 1.4210854715202004e-14 * orig && piv < INFINITY)) info = col + 1;
+        const int m = min(HB, n - 1 - col);
+        double* cj = Cc + col * W;
+        const double piv = cj[0];
+        if (info == 0 && !(piv > 1.4210854715202004e-14 * orig[col] && piv < INFINITY)) info = col + 1;
         const double ip = rcp_fast(piv);
         if (info == 0) {
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k)
-                if (need[k] <= m) {
-                    double* t = Ab + off_t[k] + col;
-                    *t = fma(-(Ab[off_p[k] + col] * ip), Ab[off_q[k] + col], *t);
-                }
+                if (need[k] <= m) cj[off_t[k]] = fma(-(cj[off_p[k]] * ip), cj[off_q[k]], cj[off_t[k]]);
         }
         __syncwarp();
     }
     if (info == 0) {
         for (int j = g; j < n; j += G) {
-            const double piv = Ab[j];
-            const double r = rsqrt_fast(piv);
-            invdiag[j] = r;
-            Ab[j] = piv * r;
+            double2* c2 = reinterpret_cast<double2*>(Cc + j * W);
+            double2 v = c2[0];
+            const double r = rsqrt_fast(v.x);
+            v.x = r;
+            v.y *= r;
+            c2[0] = v;
+#pragma unroll
+            for (int h = 1; h < W / 2; ++h) {
+                double2 w = c2[h];
+                w.x *= r;
+                w.y *= r;
+                c2[h] = w;
+            }
         }
-    }
-    __syncwarp();
-    if (info == 0) {
-        for (int d = 1; d <= b; ++d)
-            for (int j = g; j < n - d; j += G) Ab[d * n + j] *= invdiag[j];
     }
     __syncwarp();
     return info;
 }
 
-// Substitutions for a band that is exactly HB wide (b == HB), one thread per right-hand side, no bounds tests:
-// the band rectangle's slots outside the matrix (row j + d >= n) are never written and hold finite numbers, and
-// they only ever multiply the zeros the window starts with.
+// x <- (L L^T)^-1 x with the column-major factor, one thread per right-hand side.  Both passes walk the columns:
+// forward right-looking (y_j = x_j / L_jj, then x_{j+d} -= L[j+d][j] y_j in a register window), backward
+// left-looking.  Reads of x behind row n - 1 only ever meet zero entries of L.
 template <int HB>
-__device__ __forceinline__ void band_subst_exact(const double* Lb, const double* invdiag, double* x, int n) {
-    double win[HB];
+__device__ __forceinline__ void band_subst_cm(const double* Cc, double* x, int n) {
+    constexpr int W = BandCm<HB>::W;
+    double win[HB + 1];
 #pragma unroll
-    for (int d = 0; d < HB; ++d) win[d] = 0.0;
-    for (int j = 0; j < n; ++j) {                    // L y = f:  L[j][j-d] = Lb[d * n + j - d]
-        double acc = x[j];
+    for (int d = 0; d <= HB; ++d) win[d] = x[d];
+    for (int j = 0; j < n; ++j) {
+        double l[W];
+        const double2* c2 = reinterpret_cast<const double2*>(Cc + j * W);
 #pragma unroll
-        for (int d = HB; d >= 1; --d) acc = fma(-Lb[d * (n - 1) + j], win[d - 1], acc);
-        const double v = acc * invdiag[j];
+        for (int h = 0; h < W / 2; ++h) { const double2 v = c2[h]; l[2 * h] = v.x; l[2 * h + 1] = v.y; }
+        const double y = win[0] * l[0];
+        x[j] = y;
 #pragma unroll
-        for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
-        win[0] = v;
-        x[j] = v;
+        for (int d = 1; d <= HB; ++d) win[d - 1] = fma(-l[d], y, win[d]);
+        win[HB] = x[j + HB + 1];
     }
 #pragma unroll
-    for (int d = 0; d < HB; ++d) win[d] = 0.0;
-    for (int j = n - 1; j >= 0; --j) {               // L^T u = y:  L[j+d][j] = Lb[d * n + j]
+    for (int d = 0; d <= HB; ++d) win[d] = 0.0;      // win[d - 1] = u[j + d]
+    for (int j = n - 1; j >= 0; --j) {
+        double l[W];
+        const double2* c2 = reinterpret_cast<const double2*>(Cc + j * W);
+#pragma unroll
+        for (int h = 0; h < W / 2; ++h) { const double2 v = c2[h]; l[2 * h] = v.x; l[2 * h + 1] = v.y; }
         double acc = x[j];
 #pragma unroll
-        for (int d = HB; d >= 1; --d) acc = fma(-Lb[d * n + j], win[d - 1], acc);
-        const double v = acc * invdiag[j];
+        for (int d = HB; d >= 1; --d) acc = fma(-l[d], win[d - 1], acc);
+        const double u = acc * l[0];
 #pragma unroll
         for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
-        win[0] = v;
-        x[j] = v;
+        win[0] = u;
+        x[j] = u;
     }
 }
 
