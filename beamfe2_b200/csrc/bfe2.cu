@@ -800,15 +800,17 @@ k_solve(PlanDev P, BatchArgs A) {
     } else if (A.do_static) {
         stage_geometry(P, smem + L.coords, smem + L.geo, tid, nt);
     }
-    // band Cholesky of K (warp 0) and of M (warp 1); narrow bands: one thread per matrix, window in registers
+    // band Cholesky of K (warp 0) and of M (warp 1)
     auto factor = [&](bool do_k, bool do_m) {
-        if (P.hbw <= 8) {
-            if (tid == 0 && do_k) {
-                s_flag[0] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Kb, smem + L.invK, n, P.hbw)
-                                       : band_cholesky_thread<8>(smem + L.Kb, smem + L.invK, n, P.hbw);
-            } else if (tid == 32 && do_m) {
-                s_flag[1] = P.hbw <= 5 ? band_cholesky_thread<5>(smem + L.Mb, smem + L.invM, n, P.hbw)
-                                       : band_cholesky_thread<8>(smem + L.Mb, smem + L.invM, n, P.hbw);
+        if (P.hbw <= 8) {                            // narrow band: root-free elimination by the lanes of one warp
+            if (warp == 0 && do_k) {
+                const int r = P.hbw <= 5 ? band_cholesky_group<32, 5>(smem + L.Kb, smem + L.invK, n, P.hbw, lane)
+                                         : band_cholesky_group<32, 8>(smem + L.Kb, smem + L.invK, n, P.hbw, lane);
+                if (lane == 0) s_flag[0] = r;
+            } else if (warp == 1 && do_m) {
+                const int r = P.hbw <= 5 ? band_cholesky_group<32, 5>(smem + L.Mb, smem + L.invM, n, P.hbw, lane)
+                                         : band_cholesky_group<32, 8>(smem + L.Mb, smem + L.invM, n, P.hbw, lane);
+                if (lane == 0) s_flag[1] = r;
             }
         } else if (warp == 0 && do_k) {
             const int r = band_cholesky_warp(smem + L.Kb, smem + L.invK, n, P.hbw, lane);

@@ -386,6 +386,64 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
     }
 }
 
+// Row-major band ([d][n], the layout of the fused kernel): the factorisation by the G lanes of a group / warp.
+// Root-free elimination first: per column only the trailing update  A[j+p][j+q] -= A[j+p][j] A[j+q][j] / pivot
+// (lane t owns pair (p, q) number t) and ONE __syncwarp -- no scaled column has to be stored and re-read inside
+// the column loop; then one lane-parallel pass turns the unscaled columns into the Cholesky factor
+// (L[i][j] = A[i][j] / sqrt(pivot_j), invdiag[j] = 1 / L[j][j]).  invdiag holds the ORIGINAL diagonal until that
+// pass (the relative pivot test).  Returns 0 or the 1-based column of the first bad pivot, uniform per group; a
+// failed group keeps running in lockstep without storing.
+template <int G, int HB>
+__device__ __forceinline__ int band_cholesky_group(double* Ab, double* invdiag, int n, int b, int g) {
+    for (int j = g; j < n; j += G) invdiag[j] = Ab[j];
+    constexpr int NP = HB * (HB + 1) / 2, ROUNDS = (NP + G - 1) / G;
+    int off_t[ROUNDS], off_p[ROUNDS], off_q[ROUNDS], need[ROUNDS];
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const int t = g + k * G;
+        int p = 1;
+        while (p * (p + 1) / 2 <= t) ++p;            // t = p (p - 1) / 2 + (q - 1), 1 <= q <= p
+        const int q = t - p * (p - 1) / 2 + 1;
+        need[k] = (t < NP) ? p : HB + 1;             // the pair exists in a column with m >= p
+        off_p[k] = p * n;
+        off_q[k] = q * n;
+        off_t[k] = (p - q) * n + q;
+    }
+    __syncwarp();
+    int info = 0;
+    for (int col = 0; col < n; ++col) {
+        const int m = min(b, n - 1 - col);
+        const double piv = Ab[col];
+        const double orig = invdiag[col];
+        if (info == 0 && !(piv > 1.4210854715202004e-14 * orig && piv < INFINITY)) info = col + 1;
+        const double ip = rcp_fast(piv);
+        if (info == 0) {
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k)
+                if (need[k] <= m) {
+                    double* t = Ab + off_t[k] + col;
+                    *t = fma(-(Ab[off_p[k] + col] * ip), Ab[off_q[k] + col], *t);
+                }
+        }
+        __syncwarp();
+    }
+    if (info == 0) {
+        for (int j = g; j < n; j += G) {
+            const double piv = Ab[j];
+            const double r = rsqrt_fast(piv);
+            invdiag[j] = r;
+            Ab[j] = piv * r;
+        }
+    }
+    __syncwarp();
+    if (info == 0) {
+        for (int d = 1; d <= b; ++d)
+            for (int j = g; j < n - d; j += G) Ab[d * n + j] *= invdiag[j];
+    }
+    __syncwarp();
+    return info;
+}
+
 // ---- column-major band for the group kernel: column j is W = HB + 1 (rounded up to even) consecutive doubles
 //      Cc[j * W + d] = A[j + d][j], 16-byte aligned, entries outside the band or the matrix are zero.  After the
 //      factorisation slot d = 0 holds 1 / L[j][j] and d >= 1 holds L[j + d][j]: one substitution row is W / 2
