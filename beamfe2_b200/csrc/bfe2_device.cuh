@@ -302,46 +302,8 @@ __device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, i
     return 0;
 }
 
-// ---- narrow bands (hbw <= HB <= 8): the same factorisation / substitutions by ONE THREAD with the active
-//      window in registers.  The dependent chain per column is rsqrt -> mul -> fma (no shared-memory round
-//      trip, no warp sync), and per substitution row one fma + one mul: these stages are pure latency, and
-//      their latency is time the block does not spend in the Jacobi sweeps.
-template <int HB>
-__device__ __forceinline__ int band_cholesky_thread(double* Ab, double* invdiag, int n, int b) {
-    double w[HB + 1][HB + 1];                        // w[i][j] = current A[col+i][col+j], j <= i
-#pragma unroll
-    for (int i = 0; i <= HB; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j)
-            w[i][j] = (i - j <= b && i < n) ? Ab[(i - j) * n + j] : 0.0;
-    for (int col = 0; col < n; ++col) {
-        const double piv = w[0][0];
-        const double orig = Ab[col];                 // the slot still holds the original diagonal
-        if (!(piv > 1.4210854715202004e-14 * orig) || !isfinite(piv)) return col + 1;
-        const double r = rsqrt_fast(piv);
-        double l[HB + 1];
-#pragma unroll
-        for (int i = 1; i <= HB; ++i) l[i] = w[i][0] * r;
-        Ab[col] = piv * r;
-        invdiag[col] = r;
-#pragma unroll
-        for (int i = 1; i <= HB; ++i)
-            if (i <= b && col + i < n) Ab[i * n + col] = l[i];
-        // trailing update and shift of the window by one row / column
-#pragma unroll
-        for (int i = 1; i <= HB; ++i)
-#pragma unroll
-            for (int j = 1; j <= i; ++j) w[i - 1][j - 1] = fma(-l[i], l[j], w[i][j]);
-        const int row = col + 1 + HB;                // new last row of the window
-#pragma unroll
-        for (int j = 0; j <= HB; ++j) {
-            const int d = HB - j;                    // A[row][col+1+j]
-            w[HB][j] = (d <= b && row < n) ? Ab[d * n + col + 1 + j] : 0.0;
-        }
-    }
-    return 0;
-}
-
+// ---- narrow bands (hbw <= HB <= 8): substitutions by ONE THREAD per right-hand side with the active window in
+//      registers: per row one fma + one mul on the critical path, no shared-memory round trip, no sync.
 // x <- (L L^T)^-1 x (FWD && BWD) or x <- L^-T x (BWD only); xin/xout may alias; stride = distance of rows
 template <int HB, bool FWD, bool BWD>
 __device__ __forceinline__ void band_subst_thread(const double* Lb, const double* invdiag, double* x, int stride,
