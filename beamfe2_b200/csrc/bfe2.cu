@@ -845,7 +845,7 @@ k_solve(PlanDev P, BatchArgs A) {
                      A.r_local ? A.r_local + b * A.C * P.nE * 6 : nullptr,
                      A.u + b * A.C * P.sumdof,
                      A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr,
-                     A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt);
+                     A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt, ASSEMBLE);
     };
     int info = 0;
     if constexpr (REGS) {
@@ -871,12 +871,12 @@ k_solve(PlanDev P, BatchArgs A) {
         if (A.do_modal) {
             if (s_flag[1] == 0) {
                 double* s_W = smem + L.U;
-                stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt, early_k ? &kcol : nullptr);
+                stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt, early_k ? &kcol : nullptr, ASSEMBLE);
                 sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
                 if (sw != INT_MIN) {
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
                                             A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr,
-                                            tid, nt, true);
+                                            tid, nt, true, ASSEMBLE);
                 }
                 __syncthreads();
             }

@@ -305,7 +305,9 @@ __device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, i
 // ---- narrow bands (hbw <= HB <= 8): substitutions by ONE THREAD per right-hand side with the active window in
 //      registers: per row one fma + one mul on the critical path, no shared-memory round trip, no sync.
 // x <- (L L^T)^-1 x (FWD && BWD) or x <- L^-T x (BWD only); xin/xout may alias; stride = distance of rows
-template <int HB, bool FWD, bool BWD>
+// EXACT: the band is exactly HB wide and its slots outside the matrix hold finite numbers (zeros from the
+// assembly): no bounds tests -- such entries only ever multiply the zeros the window starts with.
+template <int HB, bool FWD, bool BWD, bool EXACT = false>
 __device__ __forceinline__ void band_subst_thread(const double* Lb, const double* invdiag, double* x, int stride,
                                                   int n, int b, int first = 0) {
     if (FWD) {
@@ -316,10 +318,10 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
             double far = x[j * stride];
 #pragma unroll
             for (int d = 2; d <= HB; ++d) {
-                const double lc = (d <= b && j - d >= first) ? Lb[d * n + (j - d)] : 0.0;
+                const double lc = (EXACT || (d <= b && j - d >= first)) ? Lb[d * n + (j - d)] : 0.0;
                 far = fma(-lc, win[d - 1], far);
             }
-            const double l1 = (1 <= b && j - 1 >= first) ? Lb[n + (j - 1)] : 0.0;
+            const double l1 = (EXACT || (1 <= b && j - 1 >= first)) ? Lb[n + (j - 1)] : 0.0;
             const double v = fma(-l1, win[0], far) * invdiag[j];
 #pragma unroll
             for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
@@ -335,10 +337,10 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
             double far = x[j * stride];
 #pragma unroll
             for (int d = 2; d <= HB; ++d) {
-                const double lc = (d <= b && j + d < n) ? Lb[d * n + j] : 0.0;
+                const double lc = (EXACT || (d <= b && j + d < n)) ? Lb[d * n + j] : 0.0;
                 far = fma(-lc, win[d - 1], far);
             }
-            const double l1 = (1 <= b && j + 1 < n) ? Lb[n + j] : 0.0;
+            const double l1 = (EXACT || (1 <= b && j + 1 < n)) ? Lb[n + j] : 0.0;
             const double v = fma(-l1, win[0], far) * invdiag[j];
 #pragma unroll
             for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
@@ -346,6 +348,16 @@ __device__ __forceinline__ void band_subst_thread(const double* Lb, const double
             x[j * stride] = v;
         }
     }
+}
+
+// Dispatch on the band width; `clean` = the caller guarantees zeros in the band slots outside the matrix.
+template <bool FWD, bool BWD>
+__device__ __forceinline__ void band_subst(const double* Lb, const double* invdiag, double* x, int stride, int n, int b,
+                                           int first, bool clean) {
+    if (b == 5 && clean) band_subst_thread<5, FWD, BWD, true>(Lb, invdiag, x, stride, n, b, first);
+    else if (b <= 5) band_subst_thread<5, FWD, BWD>(Lb, invdiag, x, stride, n, b, first);
+    else if (b == 8 && clean) band_subst_thread<8, FWD, BWD, true>(Lb, invdiag, x, stride, n, b, first);
+    else band_subst_thread<8, FWD, BWD>(Lb, invdiag, x, stride, n, b, first);
 }
 
 // Row-major band ([d][n], the layout of the fused kernel): the factorisation by the G lanes of a group / warp.
@@ -549,7 +561,8 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
                                              const double* s_Kb, const double* s_invK,
                                              double* s_f, double* s_ufull, double* s_ef,
                                              const double* g_f_nodal, const double* g_r_local,
-                                             double* g_u, double* g_ef, double* g_react, int tid, int nt) {
+                                             double* g_u, double* g_ef, double* g_react, int tid, int nt,
+                                             bool clean = false) {
     const int n = P.n, sumdof = P.sumdof, nE = P.nE;
     // 1. right-hand sides in free numbering
     for (int t = tid; t < C * n; t += nt) {
@@ -573,8 +586,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
     scope_sync<WARP_SCOPE>();
     // 2. one thread per load case: L L^T u = f
     for (int c = tid; c < C; c += nt) {
-        if (P.hbw <= 5) band_subst_thread<5, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
-        else if (P.hbw <= 8) band_subst_thread<8, true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw);
+        if (P.hbw <= 8) band_subst<true, true>(s_Kb, s_invK, s_f + c * n, 1, n, P.hbw, 0, clean);
         else band_solve_thread(s_Kb, s_invK, s_f + c * n, n, P.hbw);
     }
     scope_sync<WARP_SCOPE>();
@@ -1004,7 +1016,7 @@ __device__ __forceinline__ void load_k_column(const PlanDev& P, const double* s_
 // hbw <= KCOL_HB), s_Kb may already hold the factor of K.
 __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_Kb, const double* s_Mb,
                                              const double* s_invM, double* s_W, int tid, int nt,
-                                             const double (*kcol)[2 * KCOL_HB + 1] = nullptr) {
+                                             const double (*kcol)[2 * KCOL_HB + 1] = nullptr, bool clean = false) {
     const int n = P.n, b = P.hbw, LD = P.LD;
     for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
     __syncthreads();
@@ -1019,8 +1031,7 @@ __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_K
             for (int i = lo; i < j; ++i) col[i] = s_Kb[(j - i) * n + i];
             for (int i = j; i <= hi; ++i) col[i] = s_Kb[(i - j) * n + j];
         }
-        if (b <= 5) band_subst_thread<5, true, false>(s_Mb, s_invM, col, 1, n, b, lo);
-        else if (b <= 8) band_subst_thread<8, true, false>(s_Mb, s_invM, col, 1, n, b, lo);
+        if (b <= 8) band_subst<true, false>(s_Mb, s_invM, col, 1, n, b, lo, clean);
         else {
             for (int r = lo; r < n; ++r) {
                 double acc = col[r];
@@ -1032,8 +1043,7 @@ __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_K
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
         double* row = s_W + i;                        // element j of the row lives at row[j * LD]
-        if (b <= 5) band_subst_thread<5, true, false>(s_Mb, s_invM, row, LD, n, b, 0);
-        else if (b <= 8) band_subst_thread<8, true, false>(s_Mb, s_invM, row, LD, n, b, 0);
+        if (b <= 8) band_subst<true, false>(s_Mb, s_invM, row, LD, n, b, 0, clean);
         else {
             for (int r = 0; r < n; ++r) {
                 double acc = row[r * LD];
@@ -1077,7 +1087,7 @@ template <int LPP>
 __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
                                                    double* s_W, double* s_lam, int* s_order, int n_modes,
                                                    double* g_lam, double* g_phi, int tid, int nt,
-                                                   bool unit_cols = false) {
+                                                   bool unit_cols = false, bool clean = false) {
     const int n = P.n, npad = P.npad, LD = P.LD;
     // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
     for (int s = tid; s < npad; s += nt) {
@@ -1102,8 +1112,7 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
     // phi = Lk^-T w, in place in the slot; then fix the sign (largest-magnitude entry positive)
     for (int m = tid; m < n_modes; m += nt) {
         double* w = s_W + s_order[m] * LD;
-        if (P.hbw <= 5) band_subst_thread<5, false, true>(s_Kb, s_invK, w, 1, n, P.hbw);
-        else if (P.hbw <= 8) band_subst_thread<8, false, true>(s_Kb, s_invK, w, 1, n, P.hbw);
+        if (P.hbw <= 8) band_subst<false, true>(s_Kb, s_invK, w, 1, n, P.hbw, 0, clean);
         else band_backsolve_thread(s_Kb, s_invK, w, n, P.hbw);
         double best = 0.0, sign = 1.0;
         for (int r = 0; r < n; ++r) {
