@@ -40,3 +40,15 @@ def test_no_cpu_fallback_in_the_loader():
     assert 'no CPU fallback' in src and 'raise Bfe2Error' in src
     from beamfe2_b200 import _lib
     assert os.path.basename(_lib.LIB_PATH) == 'libbfe2.so' or os.environ.get('BFE2_LIB')
+
+
+def test_every_product_module_imports_on_a_cpu_only_machine():
+    """Importing the package (ctypes loader, drop-in classes, subspace-iteration paths) must not need a GPU;
+    only calling a solver does."""
+    import importlib
+    for name in ('beamfe2_b200', 'beamfe2_b200.batch', 'beamfe2_b200.beam', 'beamfe2_b200.frame_modes',
+                 'beamfe2_b200.dist', 'beamfe2_b200.sweep', 'beamfe2_b200.Solver', 'beamfe2_b200.Structure'):
+        importlib.import_module(name)
+    from beamfe2_b200.beam import LargeBeam, SubspaceIteration
+    from beamfe2_b200.frame_modes import FrameModes
+    assert issubclass(LargeBeam, SubspaceIteration) and issubclass(FrameModes, SubspaceIteration)
