@@ -25,7 +25,7 @@ plan = Plan.from_supports(21, conn, sup)
 fixed = orc.positions_to_eliminate(sup)
 free = torch.as_tensor(plan.pos_of_free.astype(np.int64), device=dev)
 eps = np.finfo(float).eps
-worst = dict(u=0.0, lam=0.0, sweeps=0, eq=0.0)
+worst = dict(u=0.0, lam=0.0, sweeps=0, eq=0.0, static_vs_fused=0.0)
 for shard in range(100, 100 + args.shards):
     P = sweep.p20_draw_params(args.batch, shard=shard)
     pk = sweep.p20_pack(torch.from_numpy(P).to(dev))
@@ -37,6 +37,14 @@ for shard in range(100, 100 + args.shards):
     eq = float((react[:, :, free].abs().amax(dim=(1, 2)) / react.abs().amax(dim=(1, 2))).max())
     worst['eq'] = max(worst['eq'], eq)
     worst['sweeps'] = max(worst['sweeps'], int(out['sweeps'].max()))
+    # the static-only kernel (16 lanes per structure) against the static part of the fused kernel, every structure
+    so = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], modal=False)
+    assert bool((so['info'] == 0).all())
+    for key in ('u', 'endforces', 'reactions'):
+        dv = float(((so[key] - out[key]).abs().amax(dim=tuple(range(1, out[key].dim()))) /
+                    out[key].abs().amax(dim=tuple(range(1, out[key].dim())))).max())
+        worst['static_vs_fused'] = max(worst['static_vs_fused'], dv)
+    assert worst['static_vs_fused'] < 1e-9, worst
     idx = np.random.default_rng(shard).choice(args.batch, args.check, replace=False)
     h = {k: v[idx].cpu().numpy() for k, v in pk.items()}
     o = orc.solve_batch(conn, fixed, h['coords'], h['props'], h['nodal_mass'], h['f_nodal'], h['r_local'], n_modes=10)
