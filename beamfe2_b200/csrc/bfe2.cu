@@ -77,6 +77,7 @@ bool jacobi_config(int n, int* rpl, int* lpp) {
     if (n <= 10) { *rpl = 5; *lpp = 2; return true; }
     if (n <= 30) { *rpl = 15; *lpp = 2; return true; }
     if (n <= 58) { *rpl = 29; *lpp = 2; return true; }
+    if (n <= 64) { *rpl = 32; *lpp = 2; return true; }    // still two columns per lane: 64 columns, 2 x 32 rows
     if (n <= 116 && n <= BFE2_MAX_JACOBI_N) { *rpl = 29; *lpp = 4; return true; }
     return false;
 }
@@ -933,14 +934,15 @@ int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStr
 
 template <bool ASSEMBLE>
 int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
-    // n <= 58: register-resident, preconditioned odd-even Jacobi (two warps per structure);
-    // 58 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
+    // n <= 64: register-resident, preconditioned odd-even Jacobi (two warps per structure);
+    // 64 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
     if (plan->lpp == 2) {
         if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
         if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
         // __launch_bounds__(64, 5): same 168 registers and 6 resident blocks as (64, 6), but ptxas schedules the
         // software-pipelined step better (+4.7 % measured); (64, 4) takes 216 registers, 4 blocks and is slower.
         if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
+        if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
     }
     if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
@@ -1071,7 +1073,7 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
     p->npad = p->n + (p->n & 1);
     if (p->n > 0 && jacobi_config(p->n, &p->rpl, &p->lpp)) {
         p->LD = p->rpl * p->lpp;
-        if (p->n <= 58) p->LD |= 1;               // register path: odd slot pitch, thread-per-slot access is conflict-free
+        if (p->n <= 64) p->LD |= 1;               // register path: odd slot pitch, thread-per-slot access is conflict-free
         p->nthreads = std::max(64, ((p->npad / 2) * p->lpp + 31) / 32 * 32);
     } else {
         p->rpl = p->lpp = 0;          // static / assembly still work; modal is refused
@@ -1278,7 +1280,7 @@ int bfe2_plan_create_dense(bfe2_plan** out, int32_t n) {
     p->npad = n + (n & 1);
     jacobi_config(n, &p->rpl, &p->lpp);
     p->LD = p->rpl * p->lpp;
-    if (p->n <= 58) p->LD |= 1;
+    if (p->n <= 64) p->LD |= 1;
     p->nthreads = 64;
     *out = p;
     return 0;

@@ -669,7 +669,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
 //   a zero dummy column.  LPP lanes share a pair (each holds RPL rows of both columns in registers).
 // ------------------------------------------------------------------------------------------------
 #define BFE2_JACOBI_TOL 1.0e-15
-#define BFE2_JACOBI_TAU 2.5e-9             // 2 n tau^2 < tol for n <= 58 (the register path)
+#define BFE2_JACOBI_TAU 2.5e-9             // 2 n tau^2 < tol for n <= 64 (the register path)
 
 template <int RPL, int LPP>
 __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
@@ -735,7 +735,7 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage M, register-resident variant (n <= 58): the same one-sided Jacobi, but the columns never
+// Stage M, register-resident variant (n <= 64): the same one-sided Jacobi, but the columns never
 // leave the register file during the sweeps.
 //
 //   Layout: TWO warps per structure; warp h owns rows [h*RPL, (h+1)*RPL) of EVERY column, lane k owns

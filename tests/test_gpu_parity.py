@@ -417,6 +417,38 @@ def test_maximum_size_of_the_jacobi_path():
             assert int(st['info'][0]) == 0
 
 
+@pytest.mark.parametrize('n_nodes,fixed', [(20, [0, 1, 2, 58]), (21, [0, 1, 2]), (22, [0, 1, 2]), (23, [0, 1, 2, 66, 67]),
+                                            (23, [0, 1, 2])])
+def test_register_path_sizes_59_to_64_and_first_smem_size(n_nodes, fixed):
+    """n_free = 56, 60, 63, 64 run the register-resident Jacobi with 32 rows per lane (64 = no dummy column, all 32
+    lanes active); 66 is the first size on the shared-memory variant.  Same checks on both sides of the boundary."""
+    rng = np.random.default_rng(n_nodes)
+    B = 6
+    xy = np.stack([np.arange(n_nodes) * 400.0, 150.0 * np.cos(np.arange(n_nodes))], axis=1)
+    conn = np.stack([np.arange(n_nodes - 1), np.arange(1, n_nodes)], axis=1).astype(np.int32)
+    coords = xy[None] + rng.uniform(-20, 20, (B, n_nodes, 2))
+    props = np.tile(np.array([2.1e5, 30.0, 22.5, 7.85e-9]), (B, n_nodes - 1, 1)) * rng.uniform(0.8, 1.2, (B, n_nodes - 1, 1))
+    mass = rng.uniform(0, 1e-4, (B, n_nodes, 2))
+    f = np.zeros((B, 2, 3 * n_nodes))
+    f[:, 0, -2] = -10.0
+    f[:, 1, 3 * (n_nodes // 2)] = 5.0
+    plan = Plan(n_nodes, conn, fixed)
+    out = batch.solve_fused(plan, T(coords), T(props), T(mass), T(f), None, n_modes=plan.n_free)
+    assert (out['info'] == 0).all()
+    o = orc.solve_batch(conn, fixed, coords, props, mass, f, None)
+    lam = out['lam'].cpu().numpy()
+    assert (np.abs(lam / o['lam'] - 1) < 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']).all()
+    condK = np.linalg.cond(o['Kc']).max()
+    assert util.relmax(out['u'].cpu().numpy(), o['u']) < max(1e-10, 50 * EPS * condK)
+    keep = plan.pos_of_free
+    phi = out['phi'].cpu().numpy()
+    for b in range(B):
+        Pf = phi[b][:, keep]
+        assert np.abs(Pf @ o['Mc'][b] @ Pf.T - np.eye(plan.n_free)).max() < 1e-9
+        res = o['Kc'][b] @ Pf.T - (o['Mc'][b] @ Pf.T) * lam[b][None, :]
+        assert (np.abs(res).max(axis=0) / (np.abs(o['Kc'][b]).max() * np.abs(Pf).max(axis=1))).max() < 1e-11
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
 def test_one_plan_on_two_devices():
     """A plan keeps one device copy per GPU: alternating devices must neither re-upload nor free a copy in use."""

@@ -1,0 +1,22 @@
+import sys, torch, numpy as np
+sys.path.insert(0, '/root/repo')
+from beamfe2_b200 import batch
+from beamfe2_b200.plan import Plan
+def run(nn, B):
+    xy = np.stack([np.arange(nn) * 500.0, np.zeros(nn)], 1)
+    conn = np.array([(k, k + 1) for k in range(nn - 1)], dtype=np.int32)
+    plan = Plan(nn, conn, [0, 1, 2])
+    rng = np.random.default_rng(0)
+    coords = torch.as_tensor(xy[None] + rng.uniform(-10, 10, (B, nn, 2)), device='cuda')
+    props = torch.as_tensor(np.tile(np.array([2.1e5, 30., 22.5, 7.85e-9]), (B, nn - 1, 1)) * rng.uniform(0.9, 1.1, (B, nn - 1, 1)), device='cuda')
+    out = batch.solve_fused(plan, coords, props, None, None, None, n_modes=10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        batch.solve_fused(plan, coords, props, None, None, None, n_modes=10, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print('n_free %3d  B %d  %.2f ms  %.0f structures/s  sweeps %.2f  info %d' % (plan.n_free, B, ms, B / ms * 1e3, out['sweeps'].double().mean().item(), int(out['info'].abs().sum())))
+for nn, B in ((11, 100000), (20, 100000), (21, 50000), (22, 50000), (23, 20000), (31, 20000), (39, 10000)):
+    run(nn, B)
