@@ -669,6 +669,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
 //   a zero dummy column.  LPP lanes share a pair (each holds RPL rows of both columns in registers).
 // ------------------------------------------------------------------------------------------------
 #define BFE2_JACOBI_TOL 1.0e-15
+#define BFE2_JACOBI_TAU_WIDE 2.0e-9        // 2 n tau^2 < tol for n <= 116 (the shared-memory variant)
 #define BFE2_JACOBI_TAU 2.5e-9             // 2 n tau^2 < tol for n <= 64 (the register path)
 
 template <int RPL, int LPP>
@@ -690,7 +691,7 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
     int sweeps = 0;
     bool converged = false;
     for (; sweeps < max_sweeps; ++sweeps) {
-        int rotated = 0;
+        int unsettled = 0;                         // same exit rule as the register variant, tau for n <= 116
         for (int step = 0; step < npad - 1; ++step) {
             double a = 0.0, b = 0.0, g = 0.0;
             if (active) {
@@ -711,12 +712,14 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
             }
             __syncthreads();                       // every pair has read its slots
             if (active) {
-                if (fabs(g) > BFE2_JACOBI_TOL * sqrt(a * b)) {
-                    rotated = 1;
+                const double gg = g * g, pab = a * b;
+                if (gg > (BFE2_JACOBI_TAU_WIDE * BFE2_JACOBI_TAU_WIDE) * pab) unsettled = 1;
+                if (gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab) {
                     const double zeta = (b - a) / (2.0 * g);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double c = 1.0 / sqrt(1.0 + t * t);
                     const double s = c * t;
+                    if (fabs(s) > BFE2_JACOBI_TAU_WIDE) unsettled = 1;
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
                         const double xr = x[r], yr = y[r];
@@ -729,7 +732,7 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
             }
             __syncthreads();                       // shifted slots visible before the next step
         }
-        if (!__syncthreads_or(rotated)) { ++sweeps; converged = true; break; }
+        if (!__syncthreads_or(unsettled)) { ++sweeps; converged = true; break; }
     }
     return converged ? sweeps : -sweeps;           // negative: not converged within max_sweeps
 }
