@@ -150,6 +150,12 @@ class Structure(object):
         lumped = np.array([b.mass_matrix == 'lumped' for b in self.beams], dtype=np.uint8)
         fixed = self.positions_to_eliminate if fixed is None else fixed
         p = planmod.Plan(nN, conn, fixed, lumped)
+        if p.hbw > 8 and fixed is not None and len(fixed) > 0:
+            # the node numbering of the model gives a wide band: let the plan renumber the free DOFs internally
+            # (reverse Cuthill-McKee); inputs and outputs stay in the model's numbering
+            q = planmod.Plan(nN, conn, fixed, lumped, reorder=True)
+            if q.hbw < p.hbw:
+                p = q
         coords = np.array([[float(n.x), float(n.y)] for n in nodes])
         props = np.array([[float(b.E), float(b.A), float(b.I), float(b.rho)] for b in self.beams])
         mass = np.zeros((nN, 2))

@@ -297,3 +297,20 @@ def test_solve_structures_batch_matches_single_solves():
     other = build(util.golden_models()['chopra_102'])
     with pytest.raises(ValueError):
         Solver.solve_structures([many[0], other])
+
+
+def test_pack_renumbers_wide_bands():
+    """A frame numbered column by column has a band as wide as the structure; Structure.pack() lets the plan
+    renumber the free DOFs (RCM) -- host-side only, no GPU needed."""
+    nodes = [Node.Node(ID=k + 1, coords=(1000.0 * (k % 6), 1000.0 * (k // 6))) for k in range(24)]
+    beams, bid = [], 1
+    for k in range(24):
+        if k % 6 < 5:
+            beams.append(HB.HermitianBeam2D(ID=bid, i=nodes[k], j=nodes[k + 1], E=2.1e5, I=1e6, A=1e3, rho=7.85e-9)); bid += 1
+        if k + 6 < 24:
+            beams.append(HB.HermitianBeam2D(ID=bid, i=nodes[k], j=nodes[k + 6], E=2.1e5, I=1e6, A=1e3, rho=7.85e-9)); bid += 1
+    s = Structure.Structure(beams=beams, supports={1: ['ux', 'uy', 'rotz'], 6: ['ux', 'uy', 'rotz']})
+    plan, pk = s.pack()
+    from beamfe2_b200.plan import Plan
+    plain = Plan(24, plan.conn, s.positions_to_eliminate)
+    assert plan.hbw <= plain.hbw and sorted(plan.pos_of_free.tolist()) == sorted(plain.pos_of_free.tolist())
