@@ -288,23 +288,30 @@ k_element_km(long long nE, const double* __restrict__ xi, const double* __restri
 constexpr int K2_WARPS = 8;
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
-k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
+k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mass = A.Mb_out != nullptr;
     const int per_warp = 20 * P.nE;                                        // doubles: [nE][8] K numbers, [nE][12] M
     const int nw = blockDim.x >> 5;                                        // warps (= structures in flight) per block
-    int* c_conn = reinterpret_cast<int*>(smem + (size_t)nw * per_warp);
-    int* c_pos = c_conn + 2 * P.nE;
-    int* c_ptr = c_pos + P.n;
-    int* c_conk = c_ptr + P.nslots + 1;
-    int* c_conm = c_conk + ncontrib;
-    int* c_lump = c_conm + ncontrib;
-    for (int i = tid; i < 2 * P.nE; i += blockDim.x) c_conn[i] = P.conn[i];
-    for (int i = tid; i < P.n; i += blockDim.x) c_pos[i] = P.pos_of_free[i];
-    for (int i = tid; i <= P.nslots; i += blockDim.x) c_ptr[i] = P.slot_ptr[i];
-    for (int i = tid; i < ncontrib; i += blockDim.x) { c_conk[i] = P.contrib_k[i]; c_conm[i] = P.contrib_m[i]; }
-    for (int i = tid; i < P.nE; i += blockDim.x) c_lump[i] = P.lumped[i];
+    // block-shared copy of the plan; a plan too large for it (cached == 0) is read from global memory / L2
+    const int* c_conn = P.conn;
+    const int* c_pos = P.pos_of_free;
+    const int* c_ptr = P.slot_ptr;
+    const int* c_conk = P.contrib_k;
+    const int* c_conm = P.contrib_m;
+    if (cached) {
+        int* s_conn = reinterpret_cast<int*>(smem + (size_t)nw * per_warp);
+        int* s_pos = s_conn + 2 * P.nE;
+        int* s_ptr = s_pos + P.n;
+        int* s_conk = s_ptr + P.nslots + 1;
+        int* s_conm = s_conk + ncontrib;
+        for (int i = tid; i < 2 * P.nE; i += blockDim.x) s_conn[i] = P.conn[i];
+        for (int i = tid; i < P.n; i += blockDim.x) s_pos[i] = P.pos_of_free[i];
+        for (int i = tid; i <= P.nslots; i += blockDim.x) s_ptr[i] = P.slot_ptr[i];
+        for (int i = tid; i < ncontrib; i += blockDim.x) { s_conk[i] = P.contrib_k[i]; s_conm[i] = P.contrib_m[i]; }
+        c_conn = s_conn; c_pos = s_pos; c_ptr = s_ptr; c_conk = s_conk; c_conm = s_conm;
+    }
     __syncthreads();
     double* w_k = smem + (size_t)warp * per_warp;
     double* w_m = w_k + 8 * P.nE;
@@ -316,7 +323,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib) {
             const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
             double L, cs, sn;
             beam_numbers(g_coords[2 * ni], g_coords[2 * ni + 1], g_coords[2 * nj], g_coords[2 * nj + 1], g_props[4 * e],
-                         g_props[4 * e + 1], g_props[4 * e + 2], g_props[4 * e + 3], want_mass, c_lump[e] != 0,
+                         g_props[4 * e + 1], g_props[4 * e + 2], g_props[4 * e + 3], want_mass, P.lumped[e] != 0,
                          w_k + 8 * e, w_m + 12 * e, L, cs, sn);
         }
         __syncwarp();
@@ -932,6 +939,85 @@ int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStr
     return 0;
 }
 
+// ---- static path for structures whose band does not fit the shared memory of an SM: the same stages with the
+//      per-structure arrays in a stream-ordered HBM workspace (L2-resident for a few structures at a time).
+//      Slow per structure, but it removes the size limit of the static solve (and of the first-k modal route,
+//      which applies K^-1 through bfe2_static_solve).
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(128)
+k_static_global(PlanDev P, BatchArgs A, double* ws, long long ws_stride) {
+    double* w = ws + (long long)blockIdx.x * ws_stride;
+    const SmemLayout L = make_layout(P.nN, P.nE, P.n, P.hbw, 0, 0, A.C);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const long long b = blockIdx.x;
+    const int n = P.n;
+    __shared__ int s_info;
+    copy_in(w + L.coords, A.coords + b * 2 * P.nN, 2 * P.nN, tid, nt);
+    copy_in(w + L.props, A.props + b * 4 * P.nE, 4 * P.nE, tid, nt);
+    if (!ASSEMBLE) copy_in(w + L.Kb, A.Kb_in + b * P.nslots, P.nslots, tid, nt);
+    __syncthreads();
+    if (ASSEMBLE) {
+        stage_elements_cf(P, w + L.coords, w + L.props, w + L.geo, w + L.U, w + L.U + 8 * P.nE, false, tid, nt);
+        __syncthreads();
+        stage_assemble_cf(P, w + L.U, w + L.U + 8 * P.nE, nullptr, w + L.Kb, w + L.Mb, false, tid, nt);
+    } else {
+        stage_geometry(P, w + L.coords, w + L.geo, tid, nt);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int r = P.hbw <= 5 ? band_cholesky_group<32, 5>(w + L.Kb, w + L.invK, n, P.hbw, lane)
+                    : P.hbw <= 8 ? band_cholesky_group<32, 8>(w + L.Kb, w + L.invK, n, P.hbw, lane)
+                                 : band_cholesky_warp(w + L.Kb, w + L.invK, n, P.hbw, lane);
+        if (lane == 0) s_info = r;
+    }
+    __syncthreads();
+    if (s_info != 0) {
+        if (tid == 0) A.info[b] = s_info;
+        fill_nan(A.u + b * A.C * P.sumdof, (long long)A.C * P.sumdof, tid, nt);
+        fill_nan(A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr, (long long)A.C * P.nE * 6, tid, nt);
+        fill_nan(A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, (long long)A.C * P.sumdof, tid, nt);
+        return;
+    }
+    double* s_f = w + L.U;
+    double* s_ufull = s_f + A.C * n;
+    double* s_ef = s_ufull + A.C * P.sumdof;
+    stage_static(P, A.C, w + L.props, w + L.geo, w + L.Kb, w + L.invK, s_f, s_ufull, s_ef,
+                 A.f_nodal + b * A.C * P.sumdof, A.r_local ? A.r_local + b * A.C * P.nE * 6 : nullptr,
+                 A.u + b * A.C * P.sumdof, A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr,
+                 A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt, false);
+    if (tid == 0) A.info[b] = 0;
+}
+
+template <bool ASSEMBLE>
+int launch_static_global(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
+    PlanDev P = pd;
+    P.npad = 0; P.LD = 0;
+    const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, A.C);
+    const long long stride = ((long long)L.total + 1) & ~1LL;
+    const long long chunk = std::max<long long>(1, std::min<long long>(A.B, (256LL << 20) / (stride * 8)));
+    double* ws = nullptr;
+    BFE2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)(chunk * stride * 8), stream));
+    const long long C = A.C, sd = plan->sumdof, nE = plan->nE, nN = plan->nN;
+    for (long long b0 = 0; b0 < A.B; b0 += chunk) {
+        BatchArgs Ac = A;
+        Ac.B = std::min(chunk, A.B - b0);
+        Ac.coords = A.coords + b0 * 2 * nN;
+        Ac.props = A.props + b0 * 4 * nE;
+        Ac.f_nodal = A.f_nodal + b0 * C * sd;
+        if (A.r_local) Ac.r_local = A.r_local + b0 * C * nE * 6;
+        if (A.Kb_in) Ac.Kb_in = A.Kb_in + b0 * plan->nslots;
+        Ac.u = A.u + b0 * C * sd;
+        if (A.endforces) Ac.endforces = A.endforces + b0 * C * nE * 6;
+        if (A.reactions) Ac.reactions = A.reactions + b0 * C * sd;
+        Ac.info = A.info + b0;
+        k_static_global<ASSEMBLE><<<(unsigned)Ac.B, 128, 0, stream>>>(P, Ac, ws, stride);
+    }
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, stream);
+    if (e != cudaSuccess) return fail(-100, "k_static_global launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 template <bool ASSEMBLE>
 int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     // n <= 64: register-resident, preconditioned odd-even Jacobi (two warps per structure);
@@ -1160,7 +1246,9 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
     const size_t per_warp = (size_t)(20 * plan->nE) * sizeof(double);
-    const size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + 2 * plan->ncontrib + plan->nE) * sizeof(int) + 16;
+    size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + 2 * plan->ncontrib) * sizeof(int) + 16;
+    const int cached = cache + per_warp <= 100 * 1024;     // a larger plan stays in global memory / L2
+    if (!cached) cache = 16;
     int nw = K2_WARPS;                                 // fewer warps per block when a structure's slice is large
     while (nw > 1 && nw * per_warp + cache > 110 * 1024) --nw;
     const size_t bytes = nw * per_warp + cache;
@@ -1172,7 +1260,7 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     const int resident = std::max<int>(1, (int)((227 * 1024) / (bytes + 1024)));
     const long long want = (B + nw - 1) / nw;
     const int grid = (int)std::min<long long>(want, (long long)sms * resident);
-    k_assemble<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(pd, A, plan->ncontrib);
+    k_assemble<<<grid, nw * 32, bytes, (cudaStream_t)stream>>>(pd, A, plan->ncontrib, cached);
     BFE2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1196,7 +1284,7 @@ int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb, c
     int nw = K3_WARPS;
     while (nw > 1 && nw * per_warp + cache > 110 * 1024) --nw;
     const size_t bytes = nw * per_warp + cache;
-    if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
+    if (bytes > 227 * 1024) return launch_static_global<false>(plan, pd, A, (cudaStream_t)stream);
     BFE2_CUDA(cudaFuncSetAttribute(k_static_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     int dev = 0, sms = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
@@ -1254,7 +1342,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         P.npad = 0; P.LD = 0;
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
         const size_t bytes = (size_t)L.total * sizeof(double);
-        if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory", bytes);
+        if (bytes > 227 * 1024) return launch_static_global<true>(plan, pd, A, (cudaStream_t)stream);
         auto kern = k_solve<5, 2, 64, 8, true, false>;
         BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");

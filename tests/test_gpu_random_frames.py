@@ -256,3 +256,55 @@ def _check_static_only(rng, xy, conn, fixed, C, B, reorder):
     for k, b in enumerate(pick):
         assert util.relmax(nob['u'][b].cpu().numpy(), o0['u'][k]) < tol
         assert util.relmax(nob['reactions'][b].cpu().numpy(), o0['reactions'][k]) < tol
+
+
+def test_structures_beyond_shared_memory_use_the_hbm_workspace_path():
+    """A 20 x 20 grid frame (400 nodes, ~1100 free DOFs, half bandwidth ~60 after RCM: 600 KB of band) does not
+    fit the shared memory of an SM: both static entry points run the HBM-workspace kernel, and the first-k modal
+    route (which applies K^-1 through bfe2_static_solve) works on top of it."""
+    import scipy.linalg as sla
+    from beamfe2_b200.frame_modes import FrameModes
+    rng = np.random.default_rng(2020)
+    side = 20
+    xy = np.array([(1000.0 * i, 1000.0 * j) for j in range(side) for i in range(side)]) + rng.uniform(-50, 50, (side * side, 2))
+    conn = []
+    for j in range(side):
+        for i in range(side):
+            k = j * side + i
+            if i + 1 < side:
+                conn.append((k, k + 1))
+            if j + 1 < side:
+                conn.append((k, k + side))
+    conn = np.array(conn, dtype=np.int32)
+    nN, nE = side * side, len(conn)
+    fixed = [3 * k + d for k in range(side) for d in range(3)]                  # bottom row clamped
+    plan = Plan(nN, conn, fixed, reorder=True)
+    assert plan.smem_bytes(2) > 227 * 1024
+    B, C = 2, 2
+    coords = xy[None] + rng.uniform(-5, 5, (B, nN, 2))
+    props = np.stack([rng.uniform(1.9e5, 2.2e5, (B, nE)), rng.uniform(2e3, 2e4, (B, nE)),
+                      rng.uniform(1e6, 1e8, (B, nE)), rng.uniform(7e-9, 8.5e-9, (B, nE))], axis=-1)
+    f_nodal = rng.uniform(-1e4, 1e4, (B, C, 3 * nN)) * (rng.uniform(size=(1, C, 3 * nN)) < 0.1)
+    L, _ = orc.length_direction(coords, conn)
+    q = rng.uniform(-5, 5, (B, C, nE)) * (rng.uniform(size=(1, C, nE)) < 0.3)
+    Lc = np.broadcast_to(L[:, None, :], q.shape)
+    r_local = np.zeros((B, C, nE, 6))
+    r_local[..., 1] = q * Lc / 2
+    r_local[..., 2] = q * (Lc ** 2) / 12
+    r_local[..., 4] = q * Lc / 2
+    r_local[..., 5] = -1 * q * (Lc ** 2) / 12.
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)     # noqa: E731
+    o = orc.solve_batch(conn, fixed, coords, props, np.zeros((B, nN, 2)), f_nodal, r_local, n_modes=1)
+    condK = np.linalg.cond(o['Kc']).max()
+    tol = max(1e-10, 50 * EPS * condK)
+    fused = batch.solve_fused(plan, T(coords), T(props), None, T(f_nodal), T(r_local), modal=False)
+    Kb, _ = batch.assemble_banded(plan, T(coords), T(props), None)
+    unfused = batch.static_solve(plan, Kb, T(coords), T(props), T(f_nodal), T(r_local))
+    for out in (fused, unfused):
+        assert (out['info'] == 0).all()
+        for key in ('u', 'endforces', 'reactions'):
+            assert util.relmax(out[key].cpu().numpy(), o[key]) < tol, key
+    fm = FrameModes(plan, T(coords[0]), T(props[0]), None)
+    res = fm.modes(n_modes=8)
+    w = sla.eigh(o['Kc'][0], o['Mc'][0], eigvals_only=True, subset_by_index=[0, 7])
+    assert np.abs(res['lam'].cpu().numpy() / w - 1).max() < 1e-7
