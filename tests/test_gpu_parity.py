@@ -500,3 +500,23 @@ def test_one_plan_from_two_host_threads():
         for lam, u, info in results[d]:
             assert int(info.abs().sum()) == 0
             assert torch.equal(lam, ref[0]) and torch.equal(u, ref[1])
+
+
+@pytest.mark.parametrize('modal', [True, False])
+def test_host_pipeline_equals_the_device_call(modal):
+    """The end-to-end path (pinned host buffers, chunks over three streams, ragged last chunk, staging buffers
+    reused) returns exactly what one device-resident call returns."""
+    P, pk, plan = p20_batch(1000)
+    pipe = batch.HostPipeline(plan, n_loadcases=3, n_modes=6, chunk=333, modal=modal)
+    h_in, h_out = pipe.alloc_host(1000)
+    for k in pipe.IN_KEYS:
+        h_in[k].copy_(pk[k].cpu())
+    pipe.run(h_in, h_out)
+    assert pipe.launches == 4
+    ref = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
+                            modal=modal, n_modes=6)
+    keys = ('u', 'endforces', 'reactions', 'info') + (('lam', 'phi', 'sweeps') if modal else ())
+    for k in keys:
+        assert torch.equal(h_out[k], ref[k].cpu()), k
+    bi, bo = pipe.bytes_per_structure()
+    assert bi == 8 * (42 + 80 + 42 + 189 + 360)
