@@ -61,7 +61,7 @@ struct bfe2_plan {
     int nN = 0, nE = 0, sumdof = 0, n = 0, hbw = 0, nslots = 0, ncontrib = 0;
     int npad = 0, LD = 0, rpl = 0, lpp = 0, nthreads = 0;
     std::vector<int32_t> conn, free_of_pos, pos_of_free, fixed, slot_ptr, contrib, node_ptr, node_inc;
-    std::vector<int32_t> contrib_k, contrib_m;   // contrib decoded: beam*8 + K number | beam*12 + M number, sign in bit 31
+    std::vector<int32_t> contrib_k, contrib_m;   // contrib decoded: beam*K7_PITCH + K number | beam*M12_PITCH + M number, sign in bit 31
     std::vector<uint8_t> lumped;
     // device mirrors: uploaded lazily on the first launch on a device, one copy per device (a plan may be used from
     // several devices and host threads at once, e.g. one thread per GPU); every entry point takes its own PlanDev
@@ -292,7 +292,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mass = A.Mb_out != nullptr;
-    const int per_warp = 20 * P.nE;                                        // doubles: [nE][8] K numbers, [nE][12] M
+    const int per_warp = (K7_PITCH + M12_PITCH) * P.nE;                    // doubles: [nE][7] K numbers, [nE][13] M
     const int nw = blockDim.x >> 5;                                        // warps (= structures in flight) per block
     // block-shared copy of the plan; a plan too large for it (cached == 0) is read from global memory / L2
     const int* c_conn = P.conn;
@@ -314,7 +314,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
     }
     __syncthreads();
     double* w_k = smem + (size_t)warp * per_warp;
-    double* w_m = w_k + 8 * P.nE;
+    double* w_m = w_k + K7_PITCH * P.nE;
     const long long nwarps = (long long)gridDim.x * nw;
     for (long long b = (long long)blockIdx.x * nw + warp; b < A.B; b += nwarps) {
         const double* g_coords = A.coords + b * 2 * P.nN;
@@ -324,7 +324,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
             double L, cs, sn;
             beam_numbers(g_coords[2 * ni], g_coords[2 * ni + 1], g_coords[2 * nj], g_coords[2 * nj + 1], g_props[4 * e],
                          g_props[4 * e + 1], g_props[4 * e + 2], g_props[4 * e + 3], want_mass, P.lumped[e] != 0,
-                         w_k + 8 * e, w_m + 12 * e, L, cs, sn);
+                         w_k + K7_PITCH * e, w_m + M12_PITCH * e, L, cs, sn);
         }
         __syncwarp();
         const double* g_mass = A.nodal_mass ? A.nodal_mass + b * 2 * P.nN : nullptr;
@@ -434,7 +434,7 @@ struct GroupLayout { int a, kb, per_group; };
 __host__ __device__ inline GroupLayout group_layout(int nE, int n, int band_w, int C, int G) {
     GroupLayout L;
     const int nslots = band_w * n;                // column-major band: band_w doubles per column
-    const int size_a = (8 * nE > C * n) ? 8 * nE : C * n;           // beam stiffness numbers | right-hand sides
+    const int size_a = (K7_PITCH * nE > C * n) ? K7_PITCH * nE : C * n;   // beam stiffness numbers | right-hand sides
     L.a = 5 * nE;                                 // after geo[nE][5] = 1/L, cos, sin, EA/L, EI/L
     L.kb = (L.a + size_a + 1) & ~1;               // 16-byte aligned: band [W n] + original diagonal [n] | end forces [C][nE][6]
     int tot = L.kb + ((nslots + n > 6 * C * nE) ? nslots + n : 6 * C * nE);
@@ -540,7 +540,7 @@ k_static_group(PlanDev P, BatchArgs A, int ncontrib) {
             ge[0] = iL; ge[1] = cs; ge[2] = sn; ge[3] = a; ge[4] = eil;
             if (ASSEMBLE) {
                 const double b6 = 6.0 * eil * iL, b12 = 2.0 * b6 * iL;
-                double* k7 = s_a + 8 * e;
+                double* k7 = s_a + K7_PITCH * e;
                 k7[0] = fma(a * cs, cs, (b12 * sn) * sn);
                 k7[1] = ((a - b12) * cs) * sn;
                 k7[2] = fma(a * sn, sn, (b12 * cs) * cs);
@@ -798,10 +798,10 @@ k_solve(PlanDev P, BatchArgs A) {
     if (tid < 2) s_flag[tid] = 0;
     __syncthreads();
     if (ASSEMBLE) {
-        stage_elements_cf(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + 8 * P.nE,
+        stage_elements_cf(P, smem + L.coords, smem + L.props, smem + L.geo, smem + L.U, smem + L.U + K7_PITCH * P.nE,
                           A.do_modal != 0, tid, nt);
         __syncthreads();
-        stage_assemble_cf(P, smem + L.U, smem + L.U + 8 * P.nE,
+        stage_assemble_cf(P, smem + L.U, smem + L.U + K7_PITCH * P.nE,
                           (A.do_modal && A.nodal_mass) ? smem + L.mass : nullptr, smem + L.Kb, smem + L.Mb,
                           A.do_modal != 0, tid, nt);
         __syncthreads();
@@ -957,9 +957,9 @@ k_static_global(PlanDev P, BatchArgs A, double* ws, long long ws_stride) {
     if (!ASSEMBLE) copy_in(w + L.Kb, A.Kb_in + b * P.nslots, P.nslots, tid, nt);
     __syncthreads();
     if (ASSEMBLE) {
-        stage_elements_cf(P, w + L.coords, w + L.props, w + L.geo, w + L.U, w + L.U + 8 * P.nE, false, tid, nt);
+        stage_elements_cf(P, w + L.coords, w + L.props, w + L.geo, w + L.U, w + L.U + K7_PITCH * P.nE, false, tid, nt);
         __syncthreads();
-        stage_assemble_cf(P, w + L.U, w + L.U + 8 * P.nE, nullptr, w + L.Kb, w + L.Mb, false, tid, nt);
+        stage_assemble_cf(P, w + L.U, w + L.U + K7_PITCH * P.nE, nullptr, w + L.Kb, w + L.Mb, false, tid, nt);
     } else {
         stage_geometry(P, w + L.coords, w + L.geo, tid, nt);
     }
@@ -1140,8 +1140,8 @@ int bfe2_plan_create_ex(bfe2_plan** out, int32_t n_nodes, int32_t n_elem, const 
     for (int i = 0; i < p->ncontrib; ++i) {
         const int idx = p->contrib[i], e = idx / 36;
         const int ck = h_ke7[idx % 36], cm = h_me12[idx % 36];
-        p->contrib_k[i] = (e * 8 + std::abs(ck) - 1) | (ck < 0 ? (int32_t)0x80000000 : 0);
-        p->contrib_m[i] = (e * 12 + std::abs(cm) - 1) | (cm < 0 ? (int32_t)0x80000000 : 0);
+        p->contrib_k[i] = (e * bfe2::K7_PITCH + std::abs(ck) - 1) | (ck < 0 ? (int32_t)0x80000000 : 0);
+        p->contrib_m[i] = (e * bfe2::M12_PITCH + std::abs(cm) - 1) | (cm < 0 ? (int32_t)0x80000000 : 0);
     }
     // node -> incident beam ends, beam order
     std::vector<std::vector<int32_t>> inc(n_nodes);
@@ -1245,7 +1245,7 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
-    const size_t per_warp = (size_t)(20 * plan->nE) * sizeof(double);
+    const size_t per_warp = (size_t)((K7_PITCH + M12_PITCH) * plan->nE) * sizeof(double);
     size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + 2 * plan->ncontrib) * sizeof(int) + 16;
     const int cached = cache + per_warp <= 100 * 1024;     // a larger plan stays in global memory / L2
     if (!cached) cache = 16;

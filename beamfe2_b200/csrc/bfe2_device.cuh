@@ -24,8 +24,8 @@ struct PlanDev {
     const int32_t* pos_of_free;   // [n]
     const int32_t* slot_ptr;      // [nslots+1]
     const int32_t* contrib;       // [ncontrib]  e*36 + r*6 + c
-    const int32_t* contrib_k;     // [ncontrib]  e*8 + K number, sign in bit 31 (closed-form beam matrices)
-    const int32_t* contrib_m;     // [ncontrib]  e*12 + M number, sign in bit 31
+    const int32_t* contrib_k;     // [ncontrib]  e*K7_PITCH + K number, sign in bit 31 (closed-form beam matrices)
+    const int32_t* contrib_m;     // [ncontrib]  e*M12_PITCH + M number, sign in bit 31
     const int32_t* node_ptr;      // [nN+1]
     const int32_t* node_inc;      // [2*nE]      e*2 + end
     const uint8_t* lumped;        // [nE]
@@ -178,6 +178,10 @@ __device__ __forceinline__ void beam_geometry(double xi, double yi, double xj, d
 //   M: f = rho A L / 420;  ii/jj block: f (140 c^2 + 156 s^2), -16 f c s, f (140 s^2 + 156 c^2), 22 L f s, 22 L f c,
 //      4 L^2 f;  ij block: f (70 c^2 + 54 s^2), 16 f c s, f (70 s^2 + 54 c^2), 13 L f s, 13 L f c, -3 L^2 f
 // and the plan says which of them (and with which sign) every band contribution is (contrib_k / contrib_m).
+// Pitch (doubles) of a beam's 7 stiffness / 12 mass numbers in shared memory: odd, so that the plan-driven gathers
+// of neighbouring beams fall into different banks (a pitch of 8 puts every second beam on the same one).
+constexpr int K7_PITCH = 7, M12_PITCH = 13;
+
 __device__ __forceinline__ void beam_numbers(double xi, double yi, double xj, double yj, double E, double Ar, double I,
                                              double rho, bool want_mass, bool lumped, double* k7, double* m12,
                                              double& L, double& cs, double& sn) {
@@ -228,7 +232,7 @@ __device__ __forceinline__ void stage_elements_cf(const PlanDev& P, const double
         double L, cs, sn;
         beam_numbers(s_coords[2 * ni], s_coords[2 * ni + 1], s_coords[2 * nj], s_coords[2 * nj + 1], s_props[4 * e],
                      s_props[4 * e + 1], s_props[4 * e + 2], s_props[4 * e + 3], want_mass, P.lumped[e] != 0,
-                     s_k7 + 8 * e, s_m12 + 12 * e, L, cs, sn);
+                     s_k7 + K7_PITCH * e, s_m12 + M12_PITCH * e, L, cs, sn);
         s_geo[3 * e] = L;
         s_geo[3 * e + 1] = cs;
         s_geo[3 * e + 2] = sn;
