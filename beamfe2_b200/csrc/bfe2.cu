@@ -292,7 +292,7 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mass = A.Mb_out != nullptr;
-    const int per_warp = (K7_PITCH + M12_PITCH) * P.nE;                    // doubles: [nE][7] K numbers, [nE][13] M
+    const int per_warp = (K7_PITCH + M12_PITCH) * P.nE + 2 * P.nN;         // doubles: [nE][7] K numbers, [nE][13] M, masses
     const int nw = blockDim.x >> 5;                                        // warps (= structures in flight) per block
     // block-shared copy of the plan; a plan too large for it (cached == 0) is read from global memory / L2
     const int* c_conn = P.conn;
@@ -315,10 +315,14 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
     __syncthreads();
     double* w_k = smem + (size_t)warp * per_warp;
     double* w_m = w_k + K7_PITCH * P.nE;
+    double* w_mass = w_m + M12_PITCH * P.nE;
     const long long nwarps = (long long)gridDim.x * nw;
     for (long long b = (long long)blockIdx.x * nw + warp; b < A.B; b += nwarps) {
         const double* g_coords = A.coords + b * 2 * P.nN;
         const double* g_props = A.props + b * 4 * P.nE;
+        const bool have_mass = want_mass && A.nodal_mass != nullptr;
+        if (have_mass)                                 // in flight together with the beam inputs
+            for (int i = lane; i < 2 * P.nN; i += 32) w_mass[i] = A.nodal_mass[b * 2 * P.nN + i];
         for (int e = lane; e < P.nE; e += 32) {
             const int ni = c_conn[2 * e], nj = c_conn[2 * e + 1];
             double L, cs, sn;
@@ -327,7 +331,6 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
                          w_k + K7_PITCH * e, w_m + M12_PITCH * e, L, cs, sn);
         }
         __syncwarp();
-        const double* g_mass = A.nodal_mass ? A.nodal_mass + b * 2 * P.nN : nullptr;
         for (int slot = lane; slot < P.nslots; slot += 32) {
             const int p0 = c_ptr[slot], p1 = c_ptr[slot + 1];
             double k = 0.0, m = 0.0;
@@ -346,10 +349,10 @@ k_assemble(PlanDev P, BatchArgs A, int ncontrib, int cached) {
             for (int p = p0 + 2; p < p1; ++p) add(p);
             A.Kb_out[b * P.nslots + slot] = k;
             if (want_mass) {
-                if (slot < P.n && g_mass != nullptr) {
+                if (slot < P.n && have_mass) {
                     const int pos = c_pos[slot];
                     const int dof = pos % 3;
-                    if (dof < 2) m += g_mass[2 * (pos / 3) + dof];
+                    if (dof < 2) m += w_mass[2 * (pos / 3) + dof];
                 }
                 A.Mb_out[b * P.nslots + slot] = m;
             }
@@ -1245,7 +1248,7 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
     if (int r = plan_upload(plan, &pd)) return r;
     BatchArgs A{};
     A.B = B; A.coords = coords; A.props = props; A.nodal_mass = nodal_mass; A.Kb_out = Kb; A.Mb_out = Mb;
-    const size_t per_warp = (size_t)((K7_PITCH + M12_PITCH) * plan->nE) * sizeof(double);
+    const size_t per_warp = (size_t)((K7_PITCH + M12_PITCH) * plan->nE + 2 * plan->nN) * sizeof(double);
     size_t cache = (size_t)(2 * plan->nE + plan->n + plan->nslots + 1 + 2 * plan->ncontrib) * sizeof(int) + 16;
     const int cached = cache + per_warp <= 100 * 1024;     // a larger plan stays in global memory / L2
     if (!cached) cache = 16;
