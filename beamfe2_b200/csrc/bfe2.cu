@@ -78,6 +78,10 @@ bool jacobi_config(int n, int* rpl, int* lpp) {
     if (n <= 30) { *rpl = 15; *lpp = 2; return true; }
     if (n <= 58) { *rpl = 29; *lpp = 2; return true; }
     if (n <= 64) { *rpl = 32; *lpp = 2; return true; }    // still two columns per lane: 64 columns, 2 x 32 rows
+    // shared-memory variant, four lanes per column pair: the smallest row count per lane that covers n
+    if (n <= 72) { *rpl = 18; *lpp = 4; return true; }
+    if (n <= 88) { *rpl = 22; *lpp = 4; return true; }
+    if (n <= 100) { *rpl = 25; *lpp = 4; return true; }
     if (n <= 116 && n <= BFE2_MAX_JACOBI_N) { *rpl = 29; *lpp = 4; return true; }
     return false;
 }
@@ -1033,6 +1037,9 @@ int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaS
         if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
         if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
     }
+    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 2, ASSEMBLE, false>(plan, pd, A, stream);
+    if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, false>(plan, pd, A, stream);
+    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 1, ASSEMBLE, false>(plan, pd, A, stream);
     if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
