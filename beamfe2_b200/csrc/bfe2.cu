@@ -919,7 +919,7 @@ k_solve(PlanDev P, BatchArgs A) {
         if (A.do_modal) {
             double* s_W = smem + L.U;
             stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
-            const int sw = stage_jacobi<RPL, LPP>(P, s_W, A.max_sweeps, tid);
+            const int sw = stage_jacobi<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid, nt);
             if (sw < 0) info = -2;
             if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
             stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,

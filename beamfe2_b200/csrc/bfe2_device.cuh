@@ -677,7 +677,8 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
 #define BFE2_JACOBI_TAU 2.5e-9             // 2 n tau^2 < tol for n <= 64 (the register path)
 
 template <int RPL, int LPP>
-__device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
+__device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, double* s_nrm, int max_sweeps, int tid,
+                                            int nt) {
     const int npad = P.npad, LD = P.LD;
     const int npairs = npad >> 1;
     const int pr = tid / LPP, h = tid % LPP;
@@ -695,34 +696,43 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
     int sweeps = 0;
     bool converged = false;
     for (; sweeps < max_sweeps; ++sweeps) {
+        // squared column norms, cached per slot and carried along with the columns (a' = a - t g, b' = b + t g):
+        // a step then costs one dot product instead of three; refreshed from the data every sweep
+        for (int s = tid; s < npad; s += nt) {
+            const double* w = s_W + s * LD;
+            double acc = 0.0;
+            for (int r = 0; r < LD; ++r) acc = fma(w[r], w[r], acc);
+            s_nrm[s] = acc;
+        }
+        __syncthreads();
         int unsettled = 0;                         // same exit rule as the register variant, tau for n <= 116
         for (int step = 0; step < npad - 1; ++step) {
-            double a = 0.0, b = 0.0, g = 0.0;
+            double g = 0.0;
             if (active) {
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) { x[r] = src_t[r]; y[r] = src_b[r]; }
 #pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    a = fma(x[r], x[r], a);
-                    b = fma(y[r], y[r], b);
-                    g = fma(x[r], y[r], g);
-                }
+                for (int r = 0; r < RPL; ++r) g = fma(x[r], y[r], g);
             }
 #pragma unroll
-            for (int m = 1; m < LPP; m <<= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, m);
-                b += __shfl_xor_sync(0xffffffffu, b, m);
-                g += __shfl_xor_sync(0xffffffffu, g, m);
-            }
+            for (int m = 1; m < LPP; m <<= 1) g += __shfl_xor_sync(0xffffffffu, g, m);
+            double a = s_nrm[st], b = s_nrm[sb];
             __syncthreads();                       // every pair has read its slots
             if (active) {
                 const double gg = g * g, pab = a * b;
                 if (gg > (BFE2_JACOBI_TAU_WIDE * BFE2_JACOBI_TAU_WIDE) * pab) unsettled = 1;
                 if (gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab) {
-                    const double zeta = (b - a) / (2.0 * g);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t);
-                    const double s = c * t;
+                    // same branch-free parameters as the register variant: c^2 = (1 + cos 2theta) / 2
+                    const double d = b - a, hh = 2.0 * g;
+                    const double ir = rsqrt_fast(fma(d, d, hh * hh));
+                    const double hs = (d < 0.0) ? -hh : hh;
+                    const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+                    const double ic = rsqrt_fast(c2);
+                    const double c = c2 * ic;
+                    const double s = (0.5 * hs * ir) * ic;
+                    const double tg = (s * ic) * g;
+                    a -= tg;
+                    b += tg;
                     if (fabs(s) > BFE2_JACOBI_TAU_WIDE) unsettled = 1;
 #pragma unroll
                     for (int r = 0; r < RPL; ++r) {
@@ -733,6 +743,7 @@ __device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, int m
                 }
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) { dst_t[r] = x[r]; dst_b[r] = y[r]; }
+                if (h == 0) { s_nrm[dt] = a; s_nrm[db] = b; }
             }
             __syncthreads();                       // shifted slots visible before the next step
         }
