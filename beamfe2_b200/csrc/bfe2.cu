@@ -863,13 +863,14 @@ k_solve(PlanDev P, BatchArgs A) {
                      A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt, ASSEMBLE);
     };
     int info = 0;
-    if constexpr (REGS) {
+    {
         // Modal part first, while the band of K is still unfactored:  C = Lm^-1 K Lm^-T, pivoted Cholesky
-        // C = Z Z^T and one-sided Jacobi on Z in registers; shapes phi = Lm^-T u.  Then K = Lk Lk^T for the
-        // static part (and for the "K is not positive definite" diagnosis, which wins over the modal codes).
+        // C = Z Z^T and one-sided Jacobi on Z (in registers for n <= 64, in shared memory above); shapes
+        // phi = Lm^-T u.  Then K = Lk Lk^T for the static part (and for the "K is not positive definite"
+        // diagnosis, which wins over the modal codes).
         int sw = 0;
         // narrow band: every thread keeps its column of K in registers, so that K and M are factored at the same
-        // time (threads 0 and 32) instead of one after the other
+        // time (warps 0 and 1) instead of one after the other
         const bool early_k = A.do_modal && P.hbw <= KCOL_HB && n <= nt;
         double kcol[2 * KCOL_HB + 1];
         if (early_k) {
@@ -887,7 +888,12 @@ k_solve(PlanDev P, BatchArgs A) {
             if (s_flag[1] == 0) {
                 double* s_W = smem + L.U;
                 stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt, early_k ? &kcol : nullptr, ASSEMBLE);
-                sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
+                if constexpr (REGS) {
+                    sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
+                } else {
+                    sw = pivoted_cholesky_smem(P, s_W, smem + L.lam, s_order, tid, nt)
+                             ? stage_jacobi<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid, nt) : INT_MIN;
+                }
                 if (sw != INT_MIN) {
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
                                             A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr,
@@ -905,28 +911,6 @@ k_solve(PlanDev P, BatchArgs A) {
         if (sw < 0) info = -2;
         if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
         if (A.do_static) static_stage();
-    } else {
-        factor(true, A.do_modal != 0);
-        const int infoK = s_flag[0], infoM = s_flag[1];
-        if (infoK != 0 || infoM != 0) {
-            fail_all(infoK != 0 ? infoK : -1);
-            return;
-        }
-        if (A.do_static) {
-            static_stage();
-            __syncthreads();
-        }
-        if (A.do_modal) {
-            double* s_W = smem + L.U;
-            stage_form_gt(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt);
-            const int sw = stage_jacobi<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid, nt);
-            if (sw < 0) info = -2;
-            if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
-            stage_modal_output<LPP>(P, smem + L.Kb, smem + L.invK, s_W, smem + L.lam, s_order, A.n_modes,
-                                    A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, tid, nt);
-        } else if (tid == 0 && A.sweeps) {
-            A.sweeps[b] = 0;
-        }
     }
     if (tid == 0) A.info[b] = info;
 }
@@ -935,7 +919,7 @@ template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
 int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
     PlanDev P = pd;
-    P.off = REGS ? 0 : plan->npad - plan->n;
+    P.off = 0;
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
     auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE, REGS>;

@@ -923,6 +923,67 @@ __device__ __forceinline__ bool pivoted_cholesky_regs(double (&A)[RPL], double (
     return true;
 }
 
+// The same preconditioner for the shared-memory Jacobi variant (64 < n <= 116): diagonally pivoted Cholesky of the
+// symmetric matrix in s_W (slot j = column j), in place, rows in their original order.  Per step warp 0 picks the
+// largest remaining diagonal entry (s_d = running diagonal), then thread (column j, row chunk h) subtracts
+// c[r] c[j] / pivot from its part of column j -- finished columns are skipped altogether; scaling by
+// 1 / sqrt(pivot) and the exact zeros of rows eliminated before a column are applied in one pass at the end
+// (s_step = elimination step of every index).  Returns false when a pivot is not positive.
+__device__ __forceinline__ bool pivoted_cholesky_smem(const PlanDev& P, double* s_W, double* s_d, int* s_step, int tid,
+                                                      int nt) {
+    const int n = P.n, LD = P.LD;
+    __shared__ int sh_p;
+    __shared__ double sh_dp;
+    const double NEG = -INFINITY;
+    for (int j = tid; j < P.npad; j += nt) {
+        s_d[j] = (j < n) ? s_W[j * LD + j] : NEG;
+        s_step[j] = -1;
+    }
+    const int tpc = max(1, nt / n);                  // threads per column
+    const int rc = (n + tpc - 1) / tpc;              // rows per thread
+    const int j = tid / tpc, h = tid - j * tpc;
+    const bool active = j < n;
+    const int r0 = h * rc, r1 = min(n, r0 + rc);
+    double* mine = s_W + (active ? j : 0) * LD;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (tid < 32) {
+            double best = NEG;
+            int arg = 0;
+            for (int q = tid; q < n; q += 32) {
+                const double v = s_d[q];
+                if (v > best) { best = v; arg = q; }
+            }
+            const unsigned key = best > 0.0 ? (unsigned)__double2hiint(best) : 0u;
+            const unsigned top = __reduce_max_sync(0xffffffffu, key);
+            const int src = __ffs(__ballot_sync(0xffffffffu, key == top)) - 1;
+            const int p = __shfl_sync(0xffffffffu, arg, src);
+            const double dp = __shfl_sync(0xffffffffu, best, src);
+            if (tid == 0) { sh_p = p; sh_dp = dp; }
+        }
+        __syncthreads();
+        const int p = sh_p;
+        const double dp = sh_dp;
+        if (!(dp > 0.0) || !isfinite(dp)) return false;          // uniform over the block
+        const double* cp = s_W + p * LD;
+        if (tid == 0) { s_d[p] = NEG; s_step[p] = k; }           // visible to the next pick after the barrier below
+        if (active && j != p && s_d[j] != NEG) {
+            const double mj = cp[j] * rcp_fast(dp);
+            for (int r = r0; r < r1; ++r) mine[r] = fma(-cp[r], mj, mine[r]);
+            if (h == 0) s_d[j] = fma(-cp[j], mj, s_d[j]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int kj = active ? s_step[j] : 0;
+    const double rs = active ? rsqrt_fast(mine[j]) : 0.0;
+    __syncthreads();
+    if (active)
+        for (int r = r0; r < r1; ++r) mine[r] = (s_step[r] < kj) ? 0.0 : mine[r] * rs;
+    __syncthreads();
+    return true;
+}
+
 // PRECOND: s_W holds the symmetric matrix C itself (slot j = column j); it is first replaced, in registers, by its
 // pivoted Cholesky factor Z (C = Z Z^T), and the sweeps orthogonalise the columns of Z:  Z V = U Sigma, so that
 // at convergence column k is  sqrt(lam_k) u_k  with  C u_k = lam_k u_k.  Returns INT_MIN if C is not positive
@@ -1067,31 +1128,6 @@ __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_K
                 double acc = row[r * LD];
                 for (int k = max(0, r - b); k < r; ++k) acc -= s_Mb[(r - k) * n + k] * row[k * LD];
                 row[r * LD] = acc * s_invM[r];
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Form W = G^T in the slot layout:  slot (k + off) holds row k of G = Lm^-1 Lk, off = P.off.
-// Thread j owns column j of G (forward substitution with the band factor Lm).
-__device__ __forceinline__ void stage_form_gt(const PlanDev& P, const double* s_Kb, const double* s_Mb,
-                                              const double* s_invM, double* s_W, int tid, int nt) {
-    const int n = P.n, b = P.hbw, LD = P.LD, off = P.off;
-    for (int t = tid; t < P.npad * LD; t += nt) s_W[t] = 0.0;
-    __syncthreads();
-    for (int j = tid; j < n; j += nt) {
-        // right-hand side: column j of Lk, written into the (transposed) slot layout, then L_m^-1 in place
-        double* col = s_W + off * LD + j;            // element r of the column lives at col[r * LD]
-        for (int r = j; r < n && r - j <= b; ++r) col[r * LD] = s_Kb[(r - j) * n + j];
-        if (b <= 5) band_subst_thread<5, true, false>(s_Mb, s_invM, col, LD, n, b, j);
-        else if (b <= 8) band_subst_thread<8, true, false>(s_Mb, s_invM, col, LD, n, b, j);
-        else {
-            for (int r = j; r < n; ++r) {
-                double acc = col[r * LD];
-                const int k0 = max(j, r - b);
-                for (int k = k0; k < r; ++k) acc -= s_Mb[(r - k) * n + k] * col[k * LD];
-                col[r * LD] = acc * s_invM[r];
             }
         }
     }
