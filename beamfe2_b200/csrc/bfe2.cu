@@ -166,7 +166,7 @@ int plan_upload(bfe2_plan* p, PlanDev* out) {
     const int32_t* base = static_cast<const int32_t*>(blob);
     PlanDev d{};
     d.nN = p->nN; d.nE = p->nE; d.sumdof = p->sumdof; d.n = p->n; d.hbw = p->hbw; d.nslots = p->nslots;
-    d.npad = p->npad; d.LD = p->LD; d.off = p->npad - p->n;
+    d.npad = p->npad; d.LD = p->LD;
     d.conn = base + off[0];
     d.free_of_pos = base + off[1];
     d.pos_of_free = base + off[2];
@@ -897,7 +897,7 @@ k_solve(PlanDev P, BatchArgs A) {
                 if (sw != INT_MIN) {
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
                                             A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr,
-                                            tid, nt, true, ASSEMBLE);
+                                            tid, nt, ASSEMBLE);
                 }
                 __syncthreads();
             }
@@ -919,7 +919,6 @@ template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
 int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
     PlanDev P = pd;
-    P.off = 0;
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
     auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE, REGS>;

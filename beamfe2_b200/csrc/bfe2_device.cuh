@@ -18,7 +18,6 @@ struct PlanDev {
     int nN, nE, sumdof, n, hbw;   // nodes, beams, 3*nN, free DOFs, half bandwidth (free numbering)
     int nslots;                   // (hbw+1)*n band slots
     int npad, LD;                 // Jacobi: even slot count >= n, leading dimension (rows, padded)
-    int off;                      // slot of row 0 of G: npad-n (dummy column in slot 0, v1) or 0 (dummy last, v2)
     const int32_t* conn;          // [nE*2]
     const int32_t* free_of_pos;   // [sumdof]
     const int32_t* pos_of_free;   // [n]
@@ -1135,13 +1134,13 @@ __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_K
 }
 
 // After convergence: eigenvalues (ascending) and the first n_modes shapes to global memory.
-// s_Lb / s_invL: the band factor the shapes are back-substituted with -- Lk (phi = Lk^-T w, columns of G^T V) or,
-// with unit_cols, Lm (phi = Lm^-T w / |w|, columns sqrt(lam) u of the preconditioned path).
+// The columns are sqrt(lam_k) u_k (C u = lam u): shapes phi_k = Lm^-T u_k, back-substituted with the band factor of M
+// passed as s_Kb / s_invK.
 template <int LPP>
 __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
                                                    double* s_W, double* s_lam, int* s_order, int n_modes,
                                                    double* g_lam, double* g_phi, int tid, int nt,
-                                                   bool unit_cols = false, bool clean = false) {
+                                                   bool clean = false) {
     const int n = P.n, npad = P.npad, LD = P.LD;
     // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
     for (int s = tid; s < npad; s += nt) {
@@ -1173,11 +1172,8 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
             const double v = fabs(w[r]);
             if (v > best) { best = v; sign = (w[r] < 0.0) ? -1.0 : 1.0; }
         }
-        if (unit_cols) {
-            sign *= rsqrt_fast(s_lam[s_order[m]]);
-            for (int r = 0; r < n; ++r) w[r] *= sign;
-        } else if (sign < 0.0)
-            for (int r = 0; r < n; ++r) w[r] = -w[r];
+        sign *= rsqrt_fast(s_lam[s_order[m]]);
+        for (int r = 0; r < n; ++r) w[r] *= sign;
     }
     __syncthreads();
     for (int t = tid; t < n_modes * P.sumdof; t += nt) {
