@@ -892,7 +892,7 @@ k_solve(PlanDev P, BatchArgs A) {
                     sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
                 } else {
                     sw = pivoted_cholesky_smem(P, s_W, smem + L.lam, s_order, tid, nt)
-                             ? stage_jacobi<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid, nt) : INT_MIN;
+                             ? stage_jacobi_oe<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid) : INT_MIN;
                 }
                 if (sw != INT_MIN) {
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,

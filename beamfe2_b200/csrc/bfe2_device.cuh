@@ -659,97 +659,21 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
 // ------------------------------------------------------------------------------------------------
 // Stage M: generalized eigenproblem K phi = lam M phi  (scipy.linalg.eigh(K, M), Solver.py:39).
 //
-//   K = Lk Lk^T, M = Lm Lm^T (band Cholesky, done by the caller);  G = Lm^-1 Lk
-//   standard form C = Lm^-1 K Lm^-T = G G^T.  The cyclic Jacobi method is applied ONE-SIDED to the
-//   factor: W = G^T V, rotating column pairs of W until they are mutually orthogonal, which is the
-//   Jacobi diagonalisation of C = (G^T)^T (G^T) without ever forming C (Veselic/Hari: the small
-//   eigenvalues keep their relative accuracy).  At convergence  lam_k = |w_k|^2  and
-//   phi_k = Lk^-T w_k  satisfies  K phi = lam M phi  with  phi^T M phi = 1  (scipy's normalisation).
+//   M = Lm Lm^T (band Cholesky, done by the caller); standard form C = Lm^-1 K Lm^-T (stage_form_a);
+//   diagonally pivoted Cholesky C = Z Z^T (Demmel-Veselic / Drmac preconditioner); the cyclic Jacobi method is
+//   then applied ONE-SIDED to the factor: Z V = U Sigma, rotating column pairs of Z until they are mutually
+//   orthogonal (Veselic/Hari: the small eigenvalues keep their relative accuracy).  At convergence
+//   lam_k = |z_k|^2, u_k = z_k / |z_k| is an eigenvector of C and  phi_k = Lm^-T u_k  satisfies
+//   K phi = lam M phi  with  phi^T M phi = 1  (scipy's normalisation).
 //
-//   Parallel ordering: round-robin tournament on npad (even) fixed SLOTS; pair p works on slots
-//   (p, npad-1-p); after every step the contents of slots 1..npad-1 rotate by one position, which the
-//   pair does by storing its two updated columns to the shifted slots.  When n is odd slot 0 holds
-//   a zero dummy column.  LPP lanes share a pair (each holds RPL rows of both columns in registers).
+//   Ordering: odd-even transposition on a line of npad (even) positions; when n is odd one position holds a
+//   zero dummy column.  n <= 64: columns in registers, two per lane, the moving column travels by warp shuffle
+//   (stage_jacobi_regs); 64 < n <= 116: LPP lanes per column pair, the moving column travels through a
+//   double-buffered exchange area in shared memory (stage_jacobi_oe).
 // ------------------------------------------------------------------------------------------------
 #define BFE2_JACOBI_TOL 1.0e-15
 #define BFE2_JACOBI_TAU_WIDE 2.0e-9        // 2 n tau^2 < tol for n <= 116 (the shared-memory variant)
 #define BFE2_JACOBI_TAU 2.5e-9             // 2 n tau^2 < tol for n <= 64 (the register path)
-
-template <int RPL, int LPP>
-__device__ __forceinline__ int stage_jacobi(const PlanDev& P, double* s_W, double* s_nrm, int max_sweeps, int tid,
-                                            int nt) {
-    const int npad = P.npad, LD = P.LD;
-    const int npairs = npad >> 1;
-    const int pr = tid / LPP, h = tid % LPP;
-    const bool active = pr < npairs;
-    const int st = active ? pr : 0;
-    const int sb = active ? (npad - 1 - pr) : 0;
-    const int dt = (st >= 1) ? st + 1 : 0;
-    const int db = (sb < npad - 1) ? sb + 1 : 1;
-    const double* src_t = s_W + st * LD + h * RPL;
-    const double* src_b = s_W + sb * LD + h * RPL;
-    double* dst_t = s_W + dt * LD + h * RPL;
-    double* dst_b = s_W + db * LD + h * RPL;
-
-    double x[RPL], y[RPL];
-    int sweeps = 0;
-    bool converged = false;
-    for (; sweeps < max_sweeps; ++sweeps) {
-        // squared column norms, cached per slot and carried along with the columns (a' = a - t g, b' = b + t g):
-        // a step then costs one dot product instead of three; refreshed from the data every sweep
-        for (int s = tid; s < npad; s += nt) {
-            const double* w = s_W + s * LD;
-            double acc = 0.0;
-            for (int r = 0; r < LD; ++r) acc = fma(w[r], w[r], acc);
-            s_nrm[s] = acc;
-        }
-        __syncthreads();
-        int unsettled = 0;                         // same exit rule as the register variant, tau for n <= 116
-        for (int step = 0; step < npad - 1; ++step) {
-            double g = 0.0;
-            if (active) {
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) { x[r] = src_t[r]; y[r] = src_b[r]; }
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) g = fma(x[r], y[r], g);
-            }
-#pragma unroll
-            for (int m = 1; m < LPP; m <<= 1) g += __shfl_xor_sync(0xffffffffu, g, m);
-            double a = s_nrm[st], b = s_nrm[sb];
-            __syncthreads();                       // every pair has read its slots
-            if (active) {
-                const double gg = g * g, pab = a * b;
-                if (gg > (BFE2_JACOBI_TAU_WIDE * BFE2_JACOBI_TAU_WIDE) * pab) unsettled = 1;
-                if (gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab) {
-                    // same branch-free parameters as the register variant: c^2 = (1 + cos 2theta) / 2
-                    const double d = b - a, hh = 2.0 * g;
-                    const double ir = rsqrt_fast(fma(d, d, hh * hh));
-                    const double hs = (d < 0.0) ? -hh : hh;
-                    const double c2 = fma(0.5 * fabs(d), ir, 0.5);
-                    const double ic = rsqrt_fast(c2);
-                    const double c = c2 * ic;
-                    const double s = (0.5 * hs * ir) * ic;
-                    const double tg = (s * ic) * g;
-                    a -= tg;
-                    b += tg;
-                    if (fabs(s) > BFE2_JACOBI_TAU_WIDE) unsettled = 1;
-#pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-                        const double xr = x[r], yr = y[r];
-                        x[r] = c * xr - s * yr;
-                        y[r] = s * xr + c * yr;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) { dst_t[r] = x[r]; dst_b[r] = y[r]; }
-                if (h == 0) { s_nrm[dt] = a; s_nrm[db] = b; }
-            }
-            __syncthreads();                       // shifted slots visible before the next step
-        }
-        if (!__syncthreads_or(unsettled)) { ++sweeps; converged = true; break; }
-    }
-    return converged ? sweeps : -sweeps;           // negative: not converged within max_sweeps
-}
 
 // ------------------------------------------------------------------------------------------------
 // Stage M, register-resident variant (n <= 64): the same one-sided Jacobi, but the columns never
@@ -920,6 +844,121 @@ __device__ __forceinline__ bool pivoted_cholesky_regs(double (&A)[RPL], double (
     }
     __syncthreads();                                  // the buffer is scratch of the sweeps from here on
     return true;
+}
+
+// Sweep engine for 64 < n <= 116: the odd-even ordering of the register variant with LPP lanes per column pair.
+// Pair p holds the columns at line positions 2p (A) and 2p+1 (B) in registers, lane h of the pair rows
+// [h RPL, (h+1) RPL).  A step rotates the resident pair, hands the moving column (B on even steps, A on odd
+// ones) and its cached norm to the neighbour pair through a double-buffered exchange area in shared memory -- ONE
+// block barrier and one column written + one column read per pair and step (the round-robin variant it replaces
+// moved both columns and needed two barriers) -- and forms the dot product of the new pairing (shuffle reduction
+// over the pair's lanes).  The last pair, which holds the two idle end positions on odd steps, exchanges them
+// (c = 0, s = -1).  s_W: slot j = column j on entry and on exit (column order is irrelevant to the caller); in
+// between its memory is the exchange area [2][npairs][LD].
+template <int RPL, int LPP>
+__device__ __forceinline__ int stage_jacobi_oe(const PlanDev& P, double* s_W, double* s_nrm, int max_sweeps, int tid) {
+    const int npad = P.npad, LD = P.LD, NP = npad >> 1;
+    const int pr = tid / LPP, h = tid % LPP;
+    const bool act = pr < NP;
+    const bool last = pr == NP - 1;
+    const int p = act ? pr : 0;
+    const int dn = (p + 1 == NP) ? 0 : p + 1;            // even steps: B comes from the pair below
+    const int up = (p == 0) ? NP - 1 : p - 1;            // odd steps: A comes from the pair above
+    double A[RPL], B[RPL];
+    {
+        const double* pa = s_W + (2 * p) * LD + h * RPL;
+        const double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            A[r] = act ? pa[r] : 0.0;
+            B[r] = act ? pb[r] : 0.0;
+        }
+    }
+    __syncthreads();                                      // the columns are in registers: s_W becomes the exchange area
+    double* mine0 = s_W + (size_t)p * LD + h * RPL;       // buffer 0; buffer 1 is NP * LD doubles further
+    const double* from_dn0 = s_W + (size_t)dn * LD + h * RPL;
+    const double* from_up0 = s_W + (size_t)up * LD + h * RPL;
+    const int half = NP * LD;
+    auto pair_sum = [&](double v) {
+#pragma unroll
+        for (int m = 1; m < LPP; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        return v;
+    };
+    int sweeps = 0;
+    bool converged = false;
+    int cur = 0;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        double nA = 0.0, nB = 0.0, g = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            nA = fma(A[r], A[r], nA);
+            nB = fma(B[r], B[r], nB);
+            g = fma(A[r], B[r], g);
+        }
+        nA = pair_sum(nA);
+        nB = pair_sum(nB);
+        g = pair_sum(g);
+        int unsettled = 0;
+        for (int step = 0; step < npad; ++step) {
+            const bool odd = step & 1;
+            const bool live = act && !(odd && last);
+            const double gg = g * g, pab = nA * nB;
+            double c = 1.0, s = 0.0;
+            if (live && gg > (BFE2_JACOBI_TAU_WIDE * BFE2_JACOBI_TAU_WIDE) * pab) unsettled = 1;
+            if (live && gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab) {
+                const double d = nB - nA, hh = 2.0 * g;
+                const double ir = rsqrt_fast(fma(d, d, hh * hh));
+                const double hs = (d < 0.0) ? -hh : hh;
+                const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+                const double ic = rsqrt_fast(c2);
+                c = c2 * ic;
+                s = (0.5 * hs * ir) * ic;
+                const double tg = (s * ic) * g;
+                nA -= tg;
+                nB += tg;
+                if (fabs(s) > BFE2_JACOBI_TAU_WIDE) unsettled = 1;
+            }
+            if (odd && last && act) {                     // exchange the two idle end columns
+                c = 0.0; s = -1.0;
+                const double t = nA; nA = nB; nB = t;
+            }
+            double* out = mine0 + cur * half;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const double sb = s * B[r], cb = c * B[r];
+                const double nb = fma(s, A[r], cb);
+                const double na = fma(c, A[r], -sb);
+                A[r] = na;
+                B[r] = nb;
+                if (act) out[r] = odd ? na : nb;
+            }
+            if (act && h == 0) s_nrm[cur * NP + p] = odd ? nA : nB;
+            __syncthreads();
+            const double* in = (odd ? from_up0 : from_dn0) + cur * half;
+            double acc = 0.0;
+            if (odd) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) { A[r] = act ? in[r] : 0.0; acc = fma(A[r], B[r], acc); }
+                nA = s_nrm[cur * NP + up];
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) { B[r] = act ? in[r] : 0.0; acc = fma(A[r], B[r], acc); }
+                nB = s_nrm[cur * NP + dn];
+            }
+            g = pair_sum(acc);
+            cur ^= 1;
+        }
+        if (!__syncthreads_or(unsettled)) { ++sweeps; converged = true; break; }
+    }
+    __syncthreads();                                      // exchange area no longer read: the columns come back
+    if (act) {
+        double* pa = s_W + (2 * p) * LD + h * RPL;
+        double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) { pa[r] = A[r]; pb[r] = B[r]; }
+    }
+    __syncthreads();
+    return converged ? sweeps : -sweeps;
 }
 
 // The same preconditioner for the shared-memory Jacobi variant (64 < n <= 116): diagonally pivoted Cholesky of the
