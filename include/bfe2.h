@@ -51,7 +51,7 @@ extern "C" {
 
 #define BFE2_VERSION 100          /* 0.1.0 */
 #define BFE2_MAX_SWEEPS 40
-#define BFE2_MAX_JACOBI_N 116     /* largest n_free the shared-memory Jacobi path accepts */
+#define BFE2_MAX_JACOBI_N 116     /* largest n_free of the all-modes path (registers up to 64, shared memory above) */
 
 typedef struct bfe2_plan bfe2_plan;
 
@@ -91,8 +91,9 @@ int  bfe2_plan_dims(const bfe2_plan* plan, int32_t* n_nodes, int32_t* n_elem, in
 int  bfe2_plan_get_array(const bfe2_plan* plan, int which, int32_t* out, int64_t capacity);
 /* bytes of dynamic shared memory per structure the fused / modal kernels need for this plan */
 size_t bfe2_plan_smem_bytes(const bfe2_plan* plan, int32_t n_loadcases);
-/* caller-owned scratch needed by the entry points below for a batch of B (currently 0: everything
- * lives in shared memory; kept so the ABI does not change when a global-memory path is added) */
+/* caller-owned scratch needed by the entry points below for a batch of B: 0.  Structures whose band does not fit
+ * the shared memory of an SM take the static path through a stream-ordered workspace the library allocates and
+ * frees on the caller's stream (cudaMallocAsync / cudaFreeAsync, <= 256 MB); nothing persistent is allocated. */
 size_t bfe2_workspace_bytes(const bfe2_plan* plan, int64_t B);
 
 /* ---- K1: element kernel (HermitianBeam_2D.py:98-120, 225-249, 284-297; helpers.py:43-69;
@@ -109,15 +110,19 @@ int bfe2_assemble_banded(bfe2_plan* plan, int64_t B, const double* coords, const
                          void* stream);
 
 /* ---- K3: banded Cholesky + forward/back substitution, end forces, reactions
- *      (Solver.py:76-87; Results.py:48-127; HermitianBeam_2D.py:336-351) ----------------------- */
+ *      (Solver.py:76-87; Results.py:48-127; HermitianBeam_2D.py:336-351).  No size limit: narrow bands run
+ *      the 16-lanes-per-structure kernel, wide ones a warp per structure, bands beyond shared memory the
+ *      HBM-workspace kernel. ---------------------------------------------------------------------- */
 int bfe2_static_solve(bfe2_plan* plan, int64_t B, int32_t C, const double* Kb,
                       const double* coords, const double* props,
                       const double* f_nodal, const double* r_local /*or NULL*/,
                       double* u, double* endforces /*or NULL*/, double* reactions /*or NULL*/,
                       int32_t* info, void* stream);
 
-/* ---- K4: generalized symmetric eigenproblem K phi = lam M phi, small n: Cholesky reduction +
- *      batched one-sided Jacobi (Solver.py:29-69).  sweeps[B] (or NULL) receives the sweep count. */
+/* ---- K4: generalized symmetric eigenproblem K phi = lam M phi, n_free <= BFE2_MAX_JACOBI_N: standard form
+ *      C = Lm^-1 K Lm^-T, pivoted Cholesky C = Z Z^T, batched one-sided Jacobi on Z (Solver.py:29-69); ALL
+ *      eigenvalues, the first n_modes shapes.  sweeps[B] (or NULL) receives the sweep count.  Larger
+ *      structures: -3 (use the first-k route, beamfe2_b200/frame_modes.py). ------------------------- */
 int bfe2_modal_solve(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Kb, const double* Mb,
                      double* lam, double* phi /*or NULL when n_modes==0*/, int32_t* info,
                      int32_t* sweeps /*or NULL*/, void* stream);
