@@ -1020,9 +1020,9 @@ int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaS
         if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
         if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
     }
-    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 2, ASSEMBLE, false>(plan, pd, A, stream);
+    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 3, ASSEMBLE, false>(plan, pd, A, stream);
     if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, false>(plan, pd, A, stream);
-    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 1, ASSEMBLE, false>(plan, pd, A, stream);
+    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 2, ASSEMBLE, false>(plan, pd, A, stream);
     if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
