@@ -278,30 +278,40 @@ __device__ __forceinline__ void stage_geometry(const PlanDev& P, const double* s
     }
 }
 
-// In-place banded Cholesky by ONE WARP.  Ab[d*n + j] = A[j+d][j], d = 0..b.  Returns 0 or the
+// In-place banded Cholesky by ONE WARP, any band width.  Ab[d*n + j] = A[j+d][j], d = 0..b.  Returns 0 or the
 // 1-based column of the first non-positive pivot (uniform across the warp).  Also writes 1/L[j][j].
+//   Root-free elimination first: in column j lane q (1 <= q <= m) owns column j+q of the trailing block and
+//   subtracts A[j+p][j] A[j+q][j] / pivot from its rows p = q..m (consecutive lanes touch consecutive addresses);
+//   column j itself is only read, so ONE __syncwarp per column suffices.  One lane-parallel pass then scales the
+//   columns into the Cholesky factor.
 __device__ __forceinline__ int band_cholesky_warp(double* Ab, double* invdiag, int n, int b, int lane) {
-    // invdiag[j] holds the ORIGINAL diagonal until column j is eliminated: a pivot that has lost all
-    // its digits (<= 64 eps * original) is reported as non-positive, i.e. numerically singular.
+    // invdiag[j] holds the ORIGINAL diagonal until the scaling pass: a pivot that has lost all its digits
+    // (<= 64 eps * original) is reported as non-positive, i.e. numerically singular.
     for (int j = lane; j < n; j += 32) invdiag[j] = Ab[j];
     __syncwarp();
     for (int j = 0; j < n; ++j) {
-        const double ajj = Ab[j];
-        if (!(ajj > 1.4210854715202004e-14 * invdiag[j]) || !isfinite(ajj)) return j + 1;
-        const double ljj = sqrt(ajj);
-        const double inv = 1.0 / ljj;
+        const double piv = Ab[j];
+        if (!(piv > 1.4210854715202004e-14 * invdiag[j] && piv < INFINITY)) return j + 1;
+        const double ip = rcp_fast(piv);
         const int m = min(b, n - 1 - j);
-        __syncwarp();
-        if (lane == 0) { Ab[j] = ljj; invdiag[j] = inv; }
-        for (int d = 1 + lane; d <= m; d += 32) Ab[d * n + j] *= inv;
-        __syncwarp();
-        // trailing update: A[j+p][j+q] -= L[j+p][j] * L[j+q][j],  1 <= q <= p <= m
-        for (int t = lane; t < m * m; t += 32) {
-            const int p = t / m + 1, q = t % m + 1;
-            if (q <= p) Ab[(p - q) * n + j + q] -= Ab[p * n + j] * Ab[q * n + j];
+        for (int q = 1 + lane; q <= m; q += 32) {
+            const double* c = Ab + q * n + j;        // c[d n] = A[j+q+d][j]
+            double* t = Ab + j + q;                  // t[d n] = A[j+q+d][j+q]
+            const double cq = c[0] * ip;
+            for (int d = 0; d <= m - q; ++d) t[d * n] = fma(-c[d * n], cq, t[d * n]);
         }
         __syncwarp();
     }
+    for (int j = lane; j < n; j += 32) {
+        const double piv = Ab[j];
+        const double r = rsqrt_fast(piv);
+        invdiag[j] = r;
+        Ab[j] = piv * r;
+    }
+    __syncwarp();
+    for (int d = 1; d <= b; ++d)
+        for (int j = lane; j < n - d; j += 32) Ab[d * n + j] *= invdiag[j];
+    __syncwarp();
     return 0;
 }
 
