@@ -19,4 +19,13 @@ for n_nodes, extra in ((12, 3), (20, 5), (30, 6)):
         batch.solve_fused(plan, coords, props, None, f, None, modal=False, out=out)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    print('nodes %d n_free %d hbw %d: %.2f ms per %d -> %.0f structures/s (info %d)' % (n_nodes, plan.n_free, plan.hbw, ms, B, B / ms * 1e3, int(out['info'].abs().sum())))
+    print('static: nodes %d n_free %d hbw %d: %.2f ms per %d -> %.0f structures/s (info %d)' % (n_nodes, plan.n_free, plan.hbw, ms, B, B / ms * 1e3, int(out['info'].abs().sum())))
+    mass = torch.as_tensor(rng.uniform(0, 1e-3, (B, n_nodes, 2)), device='cuda')
+    om = batch.solve_fused(plan, coords, props, mass, f, None, n_modes=8)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        batch.solve_fused(plan, coords, props, mass, f, None, n_modes=8, out=om)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print('static + modal:                          %.2f ms per %d -> %.0f structures/s (sweeps %.2f, info %d)' % (ms, B, B / ms * 1e3, om['sweeps'].double().mean().item(), int(om['info'].abs().sum())))
