@@ -95,6 +95,9 @@ class ModalSolver(Solver):
         out = fm.modes(n_modes=LARGE_N_MODES)
         if out.get('failed') or out['phi'] is None:
             raise np.linalg.LinAlgError('modal solve failed (subspace iteration did not produce a Ritz basis)')
+        if not out['converged'] and float(out['residual'].max().item()) > 1e-8:
+            raise np.linalg.LinAlgError('modal solve failed (subspace iteration stalled, scaled residual %.1e)'
+                                        % float(out['residual'].max().item()))
         st = self.structure
         lam = out['lam'].cpu().numpy()
         phi = out['phi'].cpu().numpy()
@@ -148,7 +151,8 @@ def solve_structures(structures, static=True, modal=True):
     for b, st in enumerate(structures):
         info = int(host['info'][b])
         s_ok = m_ok = False
-        if do_static and has_load[b] and info <= 0:
+        # info -1 / -2 invalidate only the modal outputs (include/bfe2.h); the static ones are checked as such
+        if do_static and has_load[b] and info <= 0 and np.isfinite(host['u'][b, 0]).all():
             st.results['linear static'] = Results.LinearStaticResult(
                 structure=st, displacements=[np.matrix(host['u'][b, 0]).T], endforces=host['endforces'][b, 0],
                 reactions=host['reactions'][b, 0])

@@ -16,7 +16,8 @@ SYMBOLS = (
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
     'bfe2_solve_fused',
     'bfe2_plan_create_dense', 'bfe2_sym_eig_dense',
-    'bfe2_beam_create', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve', 'bfe2_beam_matvec',
+    'bfe2_beam_create', 'bfe2_beam_create_ex', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve',
+    'bfe2_beam_solve_dd', 'bfe2_beam_matvec', 'bfe2_beam_residual', 'bfe2_beam_export_blocks',
     'bfe2_gram_workspace_bytes', 'bfe2_gram64', 'bfe2_update64',
     'bfe2_internal_actions', 'bfe2_modal_participation',
 )
@@ -35,7 +36,7 @@ def build(verbose=False):
     """Compile libbfe2.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     import subprocess
     csrc = os.path.join(_HERE, 'csrc')
-    r = subprocess.run(['make', '-C', csrc], capture_output=True, text=True)
+    r = subprocess.run(['make', '-j4', '-C', csrc], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout)
         print(r.stderr)
@@ -86,6 +87,14 @@ def lib():
     L.bfe2_sym_eig_dense.argtypes = [vp, i64] + [vp] * 8
     L.bfe2_beam_create.restype = C.c_int
     L.bfe2_beam_create.argtypes = [C.POINTER(vp), i64, vp, vp, vp, i32, vp]
+    L.bfe2_beam_create_ex.restype = C.c_int
+    L.bfe2_beam_create_ex.argtypes = [C.POINTER(vp), i64, vp, vp, vp, i32, i32, vp]
+    L.bfe2_beam_solve_dd.restype = C.c_int
+    L.bfe2_beam_solve_dd.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.bfe2_beam_residual.restype = C.c_int
+    L.bfe2_beam_residual.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.bfe2_beam_export_blocks.restype = C.c_int
+    L.bfe2_beam_export_blocks.argtypes = [vp, i32, vp, vp]
     L.bfe2_beam_destroy.restype = None
     L.bfe2_beam_destroy.argtypes = [vp]
     L.bfe2_beam_dims.restype = C.c_int

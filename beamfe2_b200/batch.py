@@ -120,6 +120,9 @@ def solve_fused(plan: Plan, coords, props, nodal_mass=None, f_nodal=None, r_loca
         t = out.get(key)
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=dev)
+        elif not t.is_contiguous():
+            # _chk() would make a contiguous COPY: the kernel would fill the copy and the caller's buffer never
+            raise ValueError('output buffer %r must be contiguous' % key)
         return _chk(t, shape, key, dtype)
 
     u = buf('u', (B, C, plan.sumdof), need=C > 0)

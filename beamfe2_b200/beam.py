@@ -171,11 +171,17 @@ class SubspaceIteration:
 
 class LargeBeam(SubspaceIteration):
     """coords [nN, 2], props [nE, 4] (E, A, I, rho): CUDA float64; nodes numbered along the chain (beam k joins
-    nodes k and k+1); fixed_positions = Structure.positions_to_eliminate (global DOF positions)."""
+    nodes k and k+1); fixed_positions = Structure.positions_to_eliminate (global DOF positions).
 
-    def __init__(self, coords, props, fixed_positions, n_partitions: int = 0):
+    precision: 'dd' (default) evaluates element matrices, factorisation and substitutions in double-double --
+    cond(K) ~ 16 n^4 makes the FP64-assembled problem meaningless at n >~ 1e4; 'fp64' runs the same kernels in
+    plain FP64 (comparison only)."""
+
+    def __init__(self, coords, props, fixed_positions, n_partitions: int = 0, precision: str = 'dd'):
         L = _lib.lib()
         assert coords.is_cuda and props.is_cuda and coords.dtype == torch.float64 and props.dtype == torch.float64
+        assert precision in ('dd', 'fp64')
+        self.precision = precision
         self.coords, self.props = coords.contiguous(), props.contiguous()
         nE = props.shape[0]
         assert coords.shape == (nE + 1, 2) and props.shape == (nE, 4)
@@ -186,8 +192,8 @@ class LargeBeam(SubspaceIteration):
         self.device = coords.device
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(L.bfe2_beam_create(C.byref(h), nE, _lib.ptr(self.coords), _lib.ptr(self.props), _lib.ptr(mask),
-                                          int(n_partitions), _sp()))
+            _lib.check(L.bfe2_beam_create_ex(C.byref(h), nE, _lib.ptr(self.coords), _lib.ptr(self.props),
+                                             _lib.ptr(mask), int(n_partitions), 1 if precision == 'dd' else 0, _sp()))
         self._h = h
         nn, nd, npart = C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(L.bfe2_beam_dims(h, C.byref(nn), C.byref(nd), C.byref(npart)))
@@ -205,13 +211,19 @@ class LargeBeam(SubspaceIteration):
             pass
 
     # ---- building blocks ---------------------------------------------------------------------
-    def solve(self, F, out=None):
-        """U = K^-1 F for F [n, nrhs] (or [n])."""
+    def solve(self, F, out=None, with_lo=False):
+        """U = K^-1 F for F [n, nrhs] (or [n]).  with_lo: also return the low words of the double-double
+        solution (U + U_lo carries ~32 digits; zeros for an fp64 handle)."""
         vec = F.dim() == 1
         F2 = F.reshape(self.n, -1).contiguous()
         U = torch.empty_like(F2) if out is None else out
+        assert U.is_contiguous() and U.shape == F2.shape
+        Ulo = torch.empty_like(F2) if with_lo else None
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().bfe2_beam_solve(self._h, F2.shape[1], _lib.ptr(F2), _lib.ptr(U), _sp()))
+            _lib.check(_lib.lib().bfe2_beam_solve_dd(self._h, F2.shape[1], _lib.ptr(F2), None, _lib.ptr(U),
+                                                     _lib.ptr(Ulo), _sp()))
+        if with_lo:
+            return (U.reshape(self.n), Ulo.reshape(self.n)) if vec else (U, Ulo)
         return U.reshape(self.n) if vec else U
 
     def matvec(self, X, mass=False, out=None):
@@ -222,10 +234,28 @@ class LargeBeam(SubspaceIteration):
             _lib.check(_lib.lib().bfe2_beam_matvec(self._h, 1 if mass else 0, X2.shape[1], _lib.ptr(X2), _lib.ptr(Y), _sp()))
         return Y.reshape(self.n) if vec else Y
 
+    def residual(self, F, U, U_lo=None):
+        """F - K (U + U_lo), evaluated in the handle's precision and rounded once."""
+        F2 = F.reshape(self.n, -1).contiguous()
+        U2 = U.reshape(self.n, -1).contiguous()
+        L2 = None if U_lo is None else U_lo.reshape(self.n, -1).contiguous()
+        R = torch.empty_like(F2)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bfe2_beam_residual(self._h, F2.shape[1], _lib.ptr(F2), _lib.ptr(U2), _lib.ptr(L2),
+                                                     _lib.ptr(R), _sp()))
+        return R.reshape(F.shape)
+
+    def blocks(self, mass=False):
+        """The stored K (or M) rounded to FP64: [n_nodes, 2, 3, 3] = blocks (k, k) and (k+1, k)."""
+        out = torch.empty((self.n_nodes, 2, 3, 3), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bfe2_beam_export_blocks(self._h, 1 if mass else 0, _lib.ptr(out), _sp()))
+        return out
+
     # ---- analyses ----------------------------------------------------------------------------
-    def static(self, f):
+    def static(self, f, with_lo=False):
         """Displacements for the load vector(s) f [n] or [n, C]; supported DOFs are forced to zero load."""
         f = f.clone()
         fm = torch.as_tensor(self.fixed_mask.astype(bool), device=self.device)
         f[fm] = 0.0
-        return self.solve(f)
+        return self.solve(f, with_lo=with_lo)

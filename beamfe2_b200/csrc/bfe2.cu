@@ -904,8 +904,20 @@ k_solve(PlanDev P, BatchArgs A) {
         }
         if (!early_k) factor(true, false);
         const int infoK = s_flag[0], infoM = s_flag[1];
-        if (infoK != 0 || infoM != 0 || sw == INT_MIN) {
-            fail_all(infoK != 0 ? infoK : (infoM != 0 ? -1 : -2));
+        if (infoK != 0) {
+            fail_all(infoK);
+            return;
+        }
+        if (infoM != 0 || sw == INT_MIN) {
+            // the mass matrix is not positive definite (-1) or the pivoted Cholesky broke down (-2): only the MODAL
+            // outputs are invalid -- K factored fine, so the static results of this structure are still delivered
+            if (tid == 0) {
+                A.info[b] = infoM != 0 ? -1 : -2;
+                if (A.sweeps) A.sweeps[b] = 0;
+            }
+            fill_nan(A.lam + b * n, n, tid, nt);
+            fill_nan(A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, (long long)A.n_modes * P.sumdof, tid, nt);
+            if (A.do_static) static_stage();
             return;
         }
         if (sw < 0) info = -2;

@@ -4,6 +4,11 @@
 //   * K and M are block tridiagonal with 3x3 blocks (one block row per node).  Supports are eliminated in
 //     place: a supported DOF keeps its row/column with K_ii = 1, M_ii = 0 and zero couplings, so u_i = 0 and
 //     the DOF numbering stays the reference's (pos = 3*node + k, Structure.py:379-393).
+//   * Precision.  cond(K) ~ 16 n^4 (1.6e21 at n = 1e5): assembled in FP64 the problem is no longer the
+//     user's problem -- every FP64 solver, scipy included, is ~100 % off on the tip deflection and the first
+//     frequencies.  The inputs are exact FP64 numbers, so by default the element matrices, the partitioned
+//     factorisation and the substitutions run in DOUBLE-DOUBLE (bfe2_dd.cuh; eps * cond ~ 2e-11).  The same
+//     kernels instantiated for plain FP64 (BFE2_BEAM_FP64) are kept for comparison.
 //   * Static solve: the sequential band Cholesky of the reference-equivalent CPU route
 //     (scipy.linalg.solveh_banded) is a dependency chain of length n.  Here the chain is cut into P
 //     partitions separated by single nodes (SPIKE / substructuring): every partition is block-Cholesky
@@ -23,9 +28,10 @@
 #include <vector>
 
 #include "../../include/bfe2.h"
-#include "bfe2_device.cuh"
+#include "bfe2_beam_core.cuh"
 
 using namespace bfe2;
+using namespace bfe2::chain;
 
 int bfe2_fail(int code, const char* fmt, ...);      // bfe2.cu
 
@@ -39,394 +45,123 @@ struct bfe2_beam {
     long long N = 0;            // nodes
     long long n = 0;            // 3 N
     int P = 1;                  // partitions
-    std::vector<int> sep;       // separator node of partitions p | p+1, size P-1
-    // device storage (one allocation)
+    int prec = BFE2_BEAM_DD;    // scalar type of the stored matrices / factor
+    // device storage (one allocation); element type double or dd according to prec
     void* blob = nullptr;
-    double *Kd, *Kl, *Md, *Ml;  // [N][9] diagonal / sub-diagonal blocks (block (k+1,k) in Kl[k])
-    double *Sinv, *G;           // [N][9] partition-local block factor
-    double *Vl, *Vr;            // [N][9] spikes
-    double *RSinv, *RG, *Rl;    // [P][9] reduced system factor, Rl = block (j, j-1)
+    void *Kd, *Kl, *Md, *Ml;    // [N][9] diagonal / sub-diagonal blocks (block (k+1,k) in Kl[k])
+    void *Sinv, *G;             // [N][9] partition-local block factor
+    void *Vl, *Vr;              // [N][9] spikes
+    void *RSinv, *RG, *Rl;      // [P][9] reduced system factor, Rl = block (j, j-1)
     int* d_sep;                 // [P+1] sep[-1] = -1 ... sep[P-1] = N, stored shifted by one
     int* d_part;                // [N] partition of an interior node, -1 for separator nodes
     int* d_info;                // [1]
     unsigned char* d_fixed;     // [3N]
+    double* lo_ws = nullptr;    // [n * lo_cap] low words of the running solution (dd only)
+    long long lo_cap = 0;
+    ~bfe2_beam() {
+        if (blob) cudaFree(blob);
+        if (lo_ws) cudaFree(lo_ws);
+    }
 };
 
 namespace {
 
-// ---- 3x3 helpers (row-major) ------------------------------------------------------------------
-__device__ __forceinline__ void m3_load(double a[9], const double* p) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) a[i] = p[i];
-}
-__device__ __forceinline__ void m3_store(double* p, const double a[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) p[i] = a[i];
-}
-// c = a * b
-__device__ __forceinline__ void m3_mul(double c[9], const double a[9], const double b[9]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
-}
-// c = a * b^T
-__device__ __forceinline__ void m3_mul_bt(double c[9], const double a[9], const double b[9]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            c[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
-}
-// c = a^T * b
-__device__ __forceinline__ void m3_mul_at(double c[9], const double a[9], const double b[9]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) c[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
-}
-// y = a x ; y = a^T x
-__device__ __forceinline__ void m3_vec(double y[3], const double a[9], const double x[3]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) y[i] = a[3 * i] * x[0] + a[3 * i + 1] * x[1] + a[3 * i + 2] * x[2];
-}
-__device__ __forceinline__ void m3_vec_t(double y[3], const double a[9], const double x[3]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) y[i] = a[i] * x[0] + a[3 + i] * x[1] + a[6 + i] * x[2];
-}
-// inverse of a symmetric positive definite 3x3 through its Cholesky factor; returns false if not SPD
-__device__ __forceinline__ bool m3_spd_inv(double inv[9], const double a[9]) {
-    const double l00s = a[0];
-    if (!(l00s > 0.0)) return false;
-    const double l00 = sqrt(l00s), i00 = 1.0 / l00;
-    const double l10 = a[3] * i00, l20 = a[6] * i00;
-    const double d1 = a[4] - l10 * l10;
-    if (!(d1 > 0.0)) return false;
-    const double l11 = sqrt(d1), i11 = 1.0 / l11;
-    const double l21 = (a[7] - l20 * l10) * i11;
-    const double d2 = a[8] - l20 * l20 - l21 * l21;
-    if (!(d2 > 0.0)) return false;
-    const double l22 = sqrt(d2), i22 = 1.0 / l22;
-    // M = L^-1 (lower): m00 = i00, m10 = -l10 i00 i11, m11 = i11, m20 = -(l20 m00 + l21 m10) i22, ...
-    const double m00 = i00, m10 = -l10 * m00 * i11, m11 = i11;
-    const double m20 = -(l20 * m00 + l21 * m10) * i22, m21 = -l21 * m11 * i22, m22 = i22;
-    // A^-1 = M^T M
-    inv[0] = m00 * m00 + m10 * m10 + m20 * m20;
-    inv[1] = inv[3] = m10 * m11 + m20 * m21;
-    inv[2] = inv[6] = m20 * m22;
-    inv[4] = m11 * m11 + m21 * m21;
-    inv[5] = inv[7] = m21 * m22;
-    inv[8] = m22 * m22;
-    return true;
-}
-
-// general 3x3 inverse (adjugate); used for the separator system, whose Schur-complement blocks are positive
-// definite only up to the cancellation error of the condensation (cond(K) ~ n^4)
-__device__ __forceinline__ bool m3_gen_inv(double inv[9], const double a[9]) {
-    const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
-    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
-    if (det == 0.0 || !isfinite(det)) return false;
-    const double r = 1.0 / det;
-    inv[0] = c00 * r; inv[1] = (a[2] * a[7] - a[1] * a[8]) * r; inv[2] = (a[1] * a[5] - a[2] * a[4]) * r;
-    inv[3] = c01 * r; inv[4] = (a[0] * a[8] - a[2] * a[6]) * r; inv[5] = (a[2] * a[3] - a[0] * a[5]) * r;
-    inv[6] = c02 * r; inv[7] = (a[1] * a[6] - a[0] * a[7]) * r; inv[8] = (a[0] * a[4] - a[1] * a[3]) * r;
-    return true;
-}
-
 // ---- assembly: thread per node ------------------------------------------------------------------
-__device__ __forceinline__ void elem_global(const double* coords, const double* props, long long e, bool mass,
-                                            double X[6][6]) {
-    double L, c, s;
-    beam_geometry(coords[2 * e], coords[2 * e + 1], coords[2 * e + 2], coords[2 * e + 3], L, c, s);
-    if (mass) me_local(X, props[4 * e + 3], props[4 * e + 1], L, false);
-    else ke_local(X, props[4 * e], props[4 * e + 1], props[4 * e + 2], L);
-    rotate_to_global(X, c, s);
-}
-
+template <class S>
 __global__ void k_beam_assemble(long long N, const double* __restrict__ coords, const double* __restrict__ props,
-                                const unsigned char* __restrict__ fixed, double* Kd, double* Kl, double* Md, double* Ml) {
+                                const unsigned char* __restrict__ fixed, S* Kd, S* Kl, S* Md, S* Ml) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool mass = pass == 1;
-        double D[9], Lb[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { D[i] = 0.0; Lb[i] = 0.0; }
-        double X[6][6];
-        if (k > 0) {                                   // element k-1 first: beam-list order (helpers.py:19-39)
-            elem_global(coords, props, k - 1, mass, X);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) D[3 * a + b] += X[3 + a][3 + b];
-        }
-        if (k < N - 1) {
-            elem_global(coords, props, k, mass, X);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    D[3 * a + b] += X[a][b];
-                    Lb[3 * a + b] = X[3 + a][b];       // block (k+1, k)
-                }
-        }
-        // supports: decouple the DOF, K_ii = 1, M_ii = 0
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const bool fa = fixed[3 * k + a] != 0;
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const bool fb = fixed[3 * k + b] != 0;
-                if (fa || fb) D[3 * a + b] = (a == b && !mass) ? 1.0 : 0.0;
-                if (k < N - 1) {
-                    const bool fr = fixed[3 * (k + 1) + a] != 0;     // row DOF belongs to node k+1
-                    if (fr || fb) Lb[3 * a + b] = 0.0;
-                }
-            }
-        }
-        m3_store((mass ? Md : Kd) + 9 * k, D);
-        m3_store((mass ? Ml : Kl) + 9 * k, Lb);
-    }
+    assemble_node<S>(k, N, coords, props, fixed, false, Kd, Kl);
+    assemble_node<S>(k, N, coords, props, fixed, true, Md, Ml);
 }
 
 // ---- partition factorisation: thread per partition ---------------------------------------------
-__global__ void k_beam_factor(int P, const int* __restrict__ sep, const double* __restrict__ Kd,
-                              const double* __restrict__ Kl, double* Sinv, double* G, int* info) {
+template <class S>
+__global__ void k_beam_factor(int P, const int* __restrict__ sep, const S* __restrict__ Kd,
+                              const S* __restrict__ Kl, S* Sinv, S* G, int* info) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const int a = sep[p] + 1, b = sep[p + 1] - 1;       // interior nodes a..b
-    double S[9], Si[9], Lk[9], Gk[9], T[9];
-    m3_load(S, Kd + 9 * (long long)a);
-    for (int k = a; k <= b; ++k) {
-        if (!m3_spd_inv(Si, S)) { atomicCAS(info, 0, k + 1); return; }
-        m3_store(Sinv + 9 * (long long)k, Si);
-        if (k < b) {
-            m3_load(Lk, Kl + 9 * (long long)k);
-            m3_mul(Gk, Lk, Si);                        // G_k = L_k S_k^-1
-            m3_store(G + 9 * (long long)k, Gk);
-            m3_mul_bt(T, Gk, Lk);                      // G_k L_k^T
-            m3_load(S, Kd + 9 * (long long)(k + 1));
-#pragma unroll
-            for (int i = 0; i < 9; ++i) S[i] -= T[i];
-        }
-    }
+    const int bad = factor_partition<S>(sep[p] + 1, sep[p + 1] - 1, Kd, Kl, Sinv, G);
+    if (bad) atomicCAS(info, 0, bad);
 }
 
-// solve T y = w in place for one 3-vector column stored with `stride` doubles between DOFs of a node and
-// `nstride` between nodes:  y(node k, dof d) at base[k*nstride + d*stride]
-__device__ __forceinline__ void part_solve_inplace(double* base, long long nstride, long long stride, int a, int b,
-                                                   const double* __restrict__ Sinv, const double* __restrict__ G) {
-    double w[3], t[3], g[9];
-    // forward: w_k = f_k - G_{k-1} w_{k-1}
-    w[0] = base[a * nstride]; w[1] = base[a * nstride + stride]; w[2] = base[a * nstride + 2 * stride];
-    for (int k = a + 1; k <= b; ++k) {
-        m3_load(g, G + 9 * (long long)(k - 1));
-        m3_vec(t, g, w);
-        double* pk = base + k * nstride;
-        w[0] = pk[0] - t[0]; w[1] = pk[stride] - t[1]; w[2] = pk[2 * stride] - t[2];
-        pk[0] = w[0]; pk[stride] = w[1]; pk[2 * stride] = w[2];
-    }
-    // diagonal + backward: y_k = S_k^-1 w_k - G_k^T y_{k+1}
-    double y[3] = {0.0, 0.0, 0.0};
-    for (int k = b; k >= a; --k) {
-        double* pk = base + k * nstride;
-        w[0] = pk[0]; w[1] = pk[stride]; w[2] = pk[2 * stride];
-        m3_load(g, Sinv + 9 * (long long)k);
-        double v[3];
-        m3_vec(v, g, w);
-        if (k < b) {
-            m3_load(g, G + 9 * (long long)k);
-            m3_vec_t(t, g, y);
-            v[0] -= t[0]; v[1] -= t[1]; v[2] -= t[2];
-        }
-        y[0] = v[0]; y[1] = v[1]; y[2] = v[2];
-        pk[0] = y[0]; pk[stride] = y[1]; pk[2 * stride] = y[2];
-    }
-}
-
-// spikes: thread per (partition, column c in 0..5); Vl/Vr hold 3x3 per node, column c of the spike
-__global__ void k_beam_spikes(int P, long long N, const int* __restrict__ sep, const double* __restrict__ Kl,
-                              const double* __restrict__ Sinv, const double* __restrict__ G, double* Vl, double* Vr) {
+// spikes: thread per (partition, column c in 0..5)
+template <class S>
+__global__ void k_beam_spikes(int P, long long N, const int* __restrict__ sep, const S* __restrict__ Kl,
+                              const S* __restrict__ Sinv, const S* __restrict__ G, S* Vl, S* Vr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P * 6) return;
-    const int p = t / 6, c = t % 6;
-    const int sl = sep[p], sr = sep[p + 1];
-    const int a = sl + 1, b = sr - 1;
-    double* V = (c < 3) ? Vl : Vr;
-    const int col = c % 3;
-    for (int k = a; k <= b; ++k)
-        for (int d = 0; d < 3; ++d) V[9 * (long long)k + 3 * d + col] = 0.0;
-    if (c < 3) {
-        if (sl < 0) return;                            // no left separator: spike is zero
-        // E_l: block at first interior node a = L[sl] (block (a, sl)); column col
-        for (int d = 0; d < 3; ++d) V[9 * (long long)a + 3 * d + col] = Kl[9 * (long long)sl + 3 * d + col];
-    } else {
-        if (sr >= N) return;
-        // E_r: block at last interior node b = L[b]^T (L[b] = block (sr, b)); column col of L^T = row col of L
-        for (int d = 0; d < 3; ++d) V[9 * (long long)b + 3 * d + col] = Kl[9 * (long long)b + 3 * col + d];
-    }
-    part_solve_inplace(V + col, 9, 3, a, b, Sinv, G);
+    spike_column<S>(t / 6, t % 6, N, sep, Kl, Sinv, G, Vl, Vr);
 }
 
 // reduced (separator) system: build + sequential block factorisation, single thread (P-1 <= a few thousand)
-__global__ void k_beam_reduced_factor(int P, const int* __restrict__ sep, const double* __restrict__ Kd,
-                                      const double* __restrict__ Kl, const double* __restrict__ Vl,
-                                      const double* __restrict__ Vr, double* RSinv, double* RG, double* Rl, int* info) {
+template <class S>
+__global__ void k_beam_reduced_factor(int P, const int* __restrict__ sep, const S* __restrict__ Kd,
+                                      const S* __restrict__ Kl, const S* __restrict__ Vl,
+                                      const S* __restrict__ Vr, S* RSinv, S* RG, S* Rl, int* info) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double S[9], Si[9], L1[9], L2[9], T[9], A[9], Gp[9];
-    for (int j = 0; j < P - 1; ++j) {
-        const long long s = sep[j + 1];
-        m3_load(S, Kd + 9 * s);
-        m3_load(L1, Kl + 9 * (s - 1));                 // block (s, s-1)
-        m3_load(L2, Kl + 9 * s);                       // block (s+1, s)
-        m3_load(A, Vr + 9 * (s - 1));
-        m3_mul(T, L1, A);                              // L[s-1] Vr[s-1]
-#pragma unroll
-        for (int i = 0; i < 9; ++i) S[i] -= T[i];
-        m3_load(A, Vl + 9 * (s + 1));
-        m3_mul_at(T, L2, A);                           // L[s]^T Vl[s+1]
-#pragma unroll
-        for (int i = 0; i < 9; ++i) S[i] -= T[i];
-        double Rlj[9];
-        m3_load(A, Vl + 9 * (s - 1));
-        m3_mul(Rlj, L1, A);                            // block (j, j-1) = -L[s-1] Vl[s-1]
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Rlj[i] = -Rlj[i];
-        m3_store(Rl + 9 * j, Rlj);
-        if (j > 0) {                                   // S_j -= Rl_j RSinv_{j-1} Rl_j^T
-            m3_load(Si, RSinv + 9 * (j - 1));
-            m3_mul(Gp, Rlj, Si);                       // RG_{j-1} = Rl_j RSinv_{j-1}
-            m3_store(RG + 9 * (j - 1), Gp);
-            m3_mul_bt(T, Gp, Rlj);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) S[i] -= T[i];
-        }
-        // symmetrise (the two spike routes agree only to rounding)
-        S[1] = S[3] = 0.5 * (S[1] + S[3]); S[2] = S[6] = 0.5 * (S[2] + S[6]); S[5] = S[7] = 0.5 * (S[5] + S[7]);
-        if (!m3_spd_inv(Si, S) && !m3_gen_inv(Si, S)) { atomicCAS(info, 0, (int)s + 1); return; }
-        m3_store(RSinv + 9 * j, Si);
-    }
+    const int bad = reduced_factor<S>(P, sep, Kd, Kl, Vl, Vr, RSinv, RG, Rl);
+    if (bad) atomicCAS(info, 0, bad);
+}
+
+// ---- solve, stage 0: U <- F (+ low words) -------------------------------------------------------
+__global__ void k_beam_load_rhs(long long count, const double* __restrict__ F, const double* __restrict__ Flo,
+                                double* U, double* Ulo) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    if (U != F) U[t] = F[t];
+    if (Ulo) Ulo[t] = Flo ? Flo[t] : 0.0;
 }
 
 // ---- solve, stage 1: thread per (partition, rhs): y = T^-1 f on the interiors (in place in U) ---
-__global__ void k_beam_solve_part(int P, int nrhs, const int* __restrict__ sep, const double* __restrict__ Sinv,
-                                  const double* __restrict__ G, double* U) {
+template <class S>
+__global__ void k_beam_solve_part(int P, const int* __restrict__ sep, const S* __restrict__ Sinv,
+                                  const S* __restrict__ G, MVec<S> U) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)P * nrhs) return;
-    const int p = (int)(t / nrhs), r = (int)(t % nrhs);
-    const int a = sep[p] + 1, b = sep[p + 1] - 1;
-    part_solve_inplace(U + r, 3LL * nrhs, nrhs, a, b, Sinv, G);
+    if (t >= (long long)P * U.nrhs) return;
+    const int p = (int)(t / U.nrhs), r = (int)(t % U.nrhs);
+    part_solve_inplace<S>(U, r, 3 * U.nrhs, U.nrhs, sep[p] + 1, sep[p + 1] - 1, Sinv, G);
 }
 
 // stage 2: thread per rhs: reduced right-hand side, sequential separator solve, x_s into U
-__global__ void k_beam_solve_reduced(int P, int nrhs, const int* __restrict__ sep, const double* __restrict__ Kl,
-                                     const double* __restrict__ RSinv, const double* __restrict__ RG, double* U) {
+template <class S>
+__global__ void k_beam_solve_reduced(int P, const int* __restrict__ sep, const S* __restrict__ Kl,
+                                     const S* __restrict__ RSinv, const S* __restrict__ RG, MVec<S> U) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrhs || P < 2) return;
-    const long long ns = 3LL * nrhs;
-    double g[3], t[3], A[9], w[3] = {0, 0, 0};
-    // forward over separators (reduced rhs built on the fly, stored in place at the separator rows)
-    for (int j = 0; j < P - 1; ++j) {
-        const long long s = sep[j + 1];
-        double* ps = U + s * ns + r;
-        g[0] = ps[0]; g[1] = ps[nrhs]; g[2] = ps[2 * nrhs];
-        double y[3];
-        const double* pm = U + (s - 1) * ns + r;
-        y[0] = pm[0]; y[1] = pm[nrhs]; y[2] = pm[2 * nrhs];
-        m3_load(A, Kl + 9 * (s - 1));
-        m3_vec(t, A, y);                               // L[s-1] y[s-1]
-        g[0] -= t[0]; g[1] -= t[1]; g[2] -= t[2];
-        const double* pp = U + (s + 1) * ns + r;
-        y[0] = pp[0]; y[1] = pp[nrhs]; y[2] = pp[2 * nrhs];
-        m3_load(A, Kl + 9 * s);
-        m3_vec_t(t, A, y);                             // L[s]^T y[s+1]
-        g[0] -= t[0]; g[1] -= t[1]; g[2] -= t[2];
-        if (j > 0) {
-            m3_load(A, RG + 9 * (j - 1));
-            m3_vec(t, A, w);                           // RG_{j-1} w_{j-1}
-            g[0] -= t[0]; g[1] -= t[1]; g[2] -= t[2];
-        }
-        w[0] = g[0]; w[1] = g[1]; w[2] = g[2];
-        ps[0] = w[0]; ps[nrhs] = w[1]; ps[2 * nrhs] = w[2];
-    }
-    double x[3] = {0, 0, 0};
-    for (int j = P - 2; j >= 0; --j) {
-        const long long s = sep[j + 1];
-        double* ps = U + s * ns + r;
-        w[0] = ps[0]; w[1] = ps[nrhs]; w[2] = ps[2 * nrhs];
-        double v[3];
-        m3_load(A, RSinv + 9 * j);
-        m3_vec(v, A, w);
-        if (j < P - 2) {
-            m3_load(A, RG + 9 * j);
-            m3_vec_t(t, A, x);
-            v[0] -= t[0]; v[1] -= t[1]; v[2] -= t[2];
-        }
-        x[0] = v[0]; x[1] = v[1]; x[2] = v[2];
-        ps[0] = x[0]; ps[nrhs] = x[1]; ps[2 * nrhs] = x[2];
-    }
+    if (r >= U.nrhs || P < 2) return;
+    solve_reduced_rhs<S>(P, r, sep, Kl, RSinv, RG, U);
 }
 
 // stage 3: thread per (interior node, rhs): x = y - Vl x_left - Vr x_right
-__global__ void k_beam_solve_fix(long long N, int P, int nrhs, const int* __restrict__ sep, const int* __restrict__ part_of,
-                                 const double* __restrict__ Vl, const double* __restrict__ Vr, double* U) {
+template <class S>
+__global__ void k_beam_solve_fix(long long N, const int* __restrict__ sep, const int* __restrict__ part_of,
+                                 const S* __restrict__ Vl, const S* __restrict__ Vr, MVec<S> U) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * nrhs) return;
-    const long long k = t / nrhs;
-    const int r = (int)(t % nrhs);
+    if (t >= N * U.nrhs) return;
+    const long long k = t / U.nrhs;
     const int p = part_of[k];
     if (p < 0) return;                                 // separator node
-    const long long ns = 3LL * nrhs;
-    const long long sl = sep[p], sr = sep[p + 1];
-    double* pk = U + k * ns + r;
-    double y[3] = {pk[0], pk[nrhs], pk[2 * nrhs]};
-    double A[9], x[3], tt[3];
-    if (sl >= 0) {
-        const double* ps = U + sl * ns + r;
-        x[0] = ps[0]; x[1] = ps[nrhs]; x[2] = ps[2 * nrhs];
-        m3_load(A, Vl + 9 * k);
-        m3_vec(tt, A, x);
-        y[0] -= tt[0]; y[1] -= tt[1]; y[2] -= tt[2];
-    }
-    if (sr < N) {
-        const double* ps = U + sr * ns + r;
-        x[0] = ps[0]; x[1] = ps[nrhs]; x[2] = ps[2 * nrhs];
-        m3_load(A, Vr + 9 * k);
-        m3_vec(tt, A, x);
-        y[0] -= tt[0]; y[1] -= tt[1]; y[2] -= tt[2];
-    }
-    pk[0] = y[0]; pk[nrhs] = y[1]; pk[2 * nrhs] = y[2];
+    solve_fix_node<S>(k, (int)(t % U.nrhs), p, N, sep, Vl, Vr, U);
 }
 
-// ---- block tridiagonal matvec: thread per (node, rhs) -------------------------------------------
-__global__ void k_beam_matvec(long long N, int nrhs, const double* __restrict__ D, const double* __restrict__ Lb,
-                              const double* __restrict__ X, double* __restrict__ Y) {
+// ---- block tridiagonal matvec / residual: thread per (node, rhs) ---------------------------------
+template <class S>
+__global__ void k_beam_matvec(long long N, const S* __restrict__ D, const S* __restrict__ Lb, MVec<S> X,
+                              const double* __restrict__ F, double* __restrict__ Y) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * nrhs) return;
-    const long long k = t / nrhs;
-    const int r = (int)(t % nrhs);
-    const long long ns = 3LL * nrhs;
-    double A[9], x[3], y[3], tt[3];
-    const double* pk = X + k * ns + r;
-    x[0] = pk[0]; x[1] = pk[nrhs]; x[2] = pk[2 * nrhs];
-    m3_load(A, D + 9 * k);
-    m3_vec(y, A, x);
-    if (k > 0) {
-        const double* pm = X + (k - 1) * ns + r;
-        x[0] = pm[0]; x[1] = pm[nrhs]; x[2] = pm[2 * nrhs];
-        m3_load(A, Lb + 9 * (k - 1));
-        m3_vec(tt, A, x);
-        y[0] += tt[0]; y[1] += tt[1]; y[2] += tt[2];
-    }
-    if (k < N - 1) {
-        const double* pp = X + (k + 1) * ns + r;
-        x[0] = pp[0]; x[1] = pp[nrhs]; x[2] = pp[2 * nrhs];
-        m3_load(A, Lb + 9 * k);
-        m3_vec_t(tt, A, x);
-        y[0] += tt[0]; y[1] += tt[1]; y[2] += tt[2];
-    }
-    double* po = Y + k * ns + r;
-    po[0] = y[0]; po[nrhs] = y[1]; po[2 * nrhs] = y[2];
+    if (t >= N * X.nrhs) return;
+    matvec_node<S>(t / X.nrhs, (int)(t % X.nrhs), N, D, Lb, X, F, Y);
+}
+
+// first block row entries of the stored K / M rounded to FP64 (introspection for tests): out[k][18] = D, Lb
+template <class S>
+__global__ void k_beam_export(long long N, const S* __restrict__ D, const S* __restrict__ Lb, double* out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * 18) return;
+    const long long k = t / 18;
+    const int i = (int)(t % 18);
+    out[t] = sc<S>::hi(i < 9 ? D[9 * k + i] : Lb[9 * k + i - 9]);
 }
 
 // ---- FP64 tensor-core contractions (q = 64) -----------------------------------------------------
@@ -528,17 +263,83 @@ __global__ void __launch_bounds__(256) k_update(long long n, const double* __res
 }  // namespace
 
 // =================================================================================================
+namespace {
+
+template <class S>
+int beam_build(bfe2_beam* h, const double* coords, const double* props, cudaStream_t st) {
+    const int T = 128, P = h->P;
+    k_beam_assemble<S><<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(h->N, coords, props, h->d_fixed, (S*)h->Kd,
+                                                                    (S*)h->Kl, (S*)h->Md, (S*)h->Ml);
+    k_beam_factor<S><<<(P + 31) / 32, 32, 0, st>>>(P, h->d_sep, (const S*)h->Kd, (const S*)h->Kl, (S*)h->Sinv,
+                                                   (S*)h->G, h->d_info);
+    k_beam_spikes<S><<<(P * 6 + 31) / 32, 32, 0, st>>>(P, h->N, h->d_sep, (const S*)h->Kl, (const S*)h->Sinv,
+                                                       (const S*)h->G, (S*)h->Vl, (S*)h->Vr);
+    k_beam_reduced_factor<S><<<1, 32, 0, st>>>(P, h->d_sep, (const S*)h->Kd, (const S*)h->Kl, (const S*)h->Vl,
+                                               (const S*)h->Vr, (S*)h->RSinv, (S*)h->RG, (S*)h->Rl, h->d_info);
+    BEAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class S>
+int beam_solve(bfe2_beam* h, int nrhs, double* U, double* Ulo, cudaStream_t st) {
+    MVec<S> mv{U, Ulo, nrhs};
+    const int T = 64;
+    const long long t1 = (long long)h->P * nrhs;
+    k_beam_solve_part<S><<<(unsigned)((t1 + T - 1) / T), T, 0, st>>>(h->P, h->d_sep, (const S*)h->Sinv,
+                                                                     (const S*)h->G, mv);
+    if (h->P > 1) {
+        k_beam_solve_reduced<S><<<(nrhs + 31) / 32, 32, 0, st>>>(h->P, h->d_sep, (const S*)h->Kl,
+                                                                 (const S*)h->RSinv, (const S*)h->RG, mv);
+        const long long t3 = h->N * nrhs;
+        k_beam_solve_fix<S><<<(unsigned)((t3 + 127) / 128), 128, 0, st>>>(h->N, h->d_sep, h->d_part,
+                                                                          (const S*)h->Vl, (const S*)h->Vr, mv);
+    }
+    BEAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class S>
+int beam_matvec(bfe2_beam* h, int which, int nrhs, const double* X, const double* Xlo, const double* F, double* Y,
+                cudaStream_t st) {
+    MVec<S> mv{const_cast<double*>(X), const_cast<double*>(Xlo), nrhs};
+    const long long t = h->N * nrhs;
+    k_beam_matvec<S><<<(unsigned)((t + 127) / 128), 128, 0, st>>>(h->N, (const S*)(which ? h->Md : h->Kd),
+                                                                  (const S*)(which ? h->Ml : h->Kl), mv, F, Y);
+    BEAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int beam_lo_workspace(bfe2_beam* h, int nrhs) {
+    if (h->prec != BFE2_BEAM_DD || nrhs <= h->lo_cap) return 0;
+    BEAM_CUDA(cudaDeviceSynchronize());                // a previous solve may still use the old buffer
+    if (h->lo_ws) cudaFree(h->lo_ws);
+    h->lo_ws = nullptr;
+    h->lo_cap = 0;
+    BEAM_CUDA(cudaMalloc(&h->lo_ws, (size_t)h->n * nrhs * sizeof(double)));
+    h->lo_cap = nrhs;
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
-int bfe2_beam_create(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
-                     const uint8_t* fixed_mask, int32_t n_partitions, void* stream) {
+int bfe2_beam_create_ex(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
+                        const uint8_t* fixed_mask, int32_t n_partitions, int32_t precision, void* stream) {
     if (!out || n_elem < 1 || !coords || !props || !fixed_mask) return bfe2_fail(-1, "bfe2_beam_create: bad argument");
+    if (precision != BFE2_BEAM_FP64 && precision != BFE2_BEAM_DD) return bfe2_fail(-1, "bfe2_beam_create: bad precision");
     *out = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     bfe2_beam* h = new bfe2_beam();
+    struct Guard {                                     // every error exit below frees the handle and its blob
+        bfe2_beam* h;
+        ~Guard() { delete h; }
+    } guard{h};
+    h->prec = precision;
     h->N = n_elem + 1;
     h->n = 3 * h->N;
-    int P = n_partitions > 0 ? n_partitions : (int)std::min<long long>(8192, std::max<long long>(1, h->N / 32));
+    // auto: partitions of ~64 nodes, at most 4096 of them (the separator system is eliminated sequentially)
+    int P = n_partitions > 0 ? n_partitions : (int)std::min<long long>(4096, std::max<long long>(1, h->N / 64));
     while (P > 1 && h->N < 3LL * P) --P;               // every partition needs at least one interior node
     h->P = P;
     std::vector<int> sep(P + 1);
@@ -550,54 +351,47 @@ int bfe2_beam_create(bfe2_beam** out, int64_t n_elem, const double* coords, cons
         for (int k = sep[p] + 1; k < sep[p + 1]; ++k) part_of[k] = p;
         if (p + 1 < P) part_of[sep[p + 1]] = -1;
     }
-    const size_t nb = (size_t)h->N * 9 * sizeof(double);
-    const size_t pb = (size_t)(P + 1) * 9 * sizeof(double);
+    const size_t es = precision == BFE2_BEAM_DD ? sizeof(dd) : sizeof(double);
+    const size_t nb = (size_t)h->N * 9 * es;
+    const size_t pb = (size_t)(P + 1) * 9 * es;
     auto r64 = [](size_t b) { return (b + 63) & ~size_t(63); };
     const size_t total = 8 * r64(nb) + 3 * r64(pb) + r64((size_t)(P + 1) * sizeof(int)) +
                          r64((size_t)h->N * sizeof(int)) + r64(sizeof(int)) + r64((size_t)h->n) + 256;
     if (cudaMalloc(&h->blob, total) != cudaSuccess) {
-        delete h;
+        h->blob = nullptr;
         return bfe2_fail(-100, "cudaMalloc of %zu bytes failed", total);
     }
     char* q = (char*)h->blob;
-    auto take = [&](size_t b) { char* r = q; q += (b + 63) & ~size_t(63); return r; };
-    h->Kd = (double*)take(nb); h->Kl = (double*)take(nb); h->Md = (double*)take(nb); h->Ml = (double*)take(nb);
-    h->Sinv = (double*)take(nb); h->G = (double*)take(nb); h->Vl = (double*)take(nb); h->Vr = (double*)take(nb);
-    h->RSinv = (double*)take(pb); h->RG = (double*)take(pb); h->Rl = (double*)take(pb);
+    auto take = [&](size_t b) { char* r = q; q += (b + 63) & ~size_t(63); return (void*)r; };
+    h->Kd = take(nb); h->Kl = take(nb); h->Md = take(nb); h->Ml = take(nb);
+    h->Sinv = take(nb); h->G = take(nb); h->Vl = take(nb); h->Vr = take(nb);
+    h->RSinv = take(pb); h->RG = take(pb); h->Rl = take(pb);
     h->d_sep = (int*)take((P + 1) * sizeof(int));
     h->d_part = (int*)take(h->N * sizeof(int));
-    int* d_part = h->d_part;
     h->d_info = (int*)take(sizeof(int));
     h->d_fixed = (unsigned char*)take(h->n);
     BEAM_CUDA(cudaMemcpyAsync(h->d_sep, sep.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    BEAM_CUDA(cudaMemcpyAsync(d_part, part_of.data(), h->N * sizeof(int), cudaMemcpyHostToDevice, st));
+    BEAM_CUDA(cudaMemcpyAsync(h->d_part, part_of.data(), h->N * sizeof(int), cudaMemcpyHostToDevice, st));
     BEAM_CUDA(cudaMemcpyAsync(h->d_fixed, fixed_mask, h->n, cudaMemcpyHostToDevice, st));
     BEAM_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), st));
     BEAM_CUDA(cudaStreamSynchronize(st));              // host vectors go out of scope
-    h->sep.assign(sep.begin(), sep.end());
-    const int T = 128;
-    k_beam_assemble<<<(unsigned)((h->N + T - 1) / T), T, 0, st>>>(h->N, coords, props, h->d_fixed, h->Kd, h->Kl, h->Md, h->Ml);
-    k_beam_factor<<<(P + T - 1) / T, T, 0, st>>>(P, h->d_sep, h->Kd, h->Kl, h->Sinv, h->G, h->d_info);
-    k_beam_spikes<<<(P * 6 + T - 1) / T, T, 0, st>>>(P, h->N, h->d_sep, h->Kl, h->Sinv, h->G, h->Vl, h->Vr);
-    k_beam_reduced_factor<<<1, 32, 0, st>>>(P, h->d_sep, h->Kd, h->Kl, h->Vl, h->Vr, h->RSinv, h->RG, h->Rl, h->d_info);
-    BEAM_CUDA(cudaGetLastError());
+    const int rc = precision == BFE2_BEAM_DD ? beam_build<dd>(h, coords, props, st) : beam_build<double>(h, coords, props, st);
+    if (rc) return rc;
     int info = 0;
     BEAM_CUDA(cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     BEAM_CUDA(cudaStreamSynchronize(st));
-    if (info != 0) {
-        cudaFree(h->blob);
-        delete h;
-        return bfe2_fail(-4, "stiffness matrix is not positive definite (node %d)", info);
-    }
+    if (info != 0) return bfe2_fail(-4, "stiffness matrix is not positive definite (node %d)", info);
+    guard.h = nullptr;
     *out = h;
     return 0;
 }
 
-void bfe2_beam_destroy(bfe2_beam* h) {
-    if (!h) return;
-    if (h->blob) cudaFree(h->blob);
-    delete h;
+int bfe2_beam_create(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
+                     const uint8_t* fixed_mask, int32_t n_partitions, void* stream) {
+    return bfe2_beam_create_ex(out, n_elem, coords, props, fixed_mask, n_partitions, BFE2_BEAM_DD, stream);
 }
+
+void bfe2_beam_destroy(bfe2_beam* h) { delete h; }
 
 int bfe2_beam_dims(const bfe2_beam* h, int64_t* n_nodes, int64_t* n_dof, int32_t* n_partitions) {
     if (!h) return bfe2_fail(-1, "beam handle is NULL");
@@ -607,29 +401,52 @@ int bfe2_beam_dims(const bfe2_beam* h, int64_t* n_nodes, int64_t* n_dof, int32_t
     return 0;
 }
 
-int bfe2_beam_solve(bfe2_beam* h, int32_t nrhs, const double* F, double* U, void* stream) {
+int bfe2_beam_solve_dd(bfe2_beam* h, int32_t nrhs, const double* F, const double* F_lo, double* U, double* U_lo,
+                       void* stream) {
     if (!h || nrhs < 1 || !F || !U) return bfe2_fail(-1, "bfe2_beam_solve: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (F != U) BEAM_CUDA(cudaMemcpyAsync(U, F, (size_t)h->n * nrhs * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    const int T = 128;
-    const int* d_part = h->d_part;
-    const long long t1 = (long long)h->P * nrhs;
-    k_beam_solve_part<<<(unsigned)((t1 + T - 1) / T), T, 0, st>>>(h->P, nrhs, h->d_sep, h->Sinv, h->G, U);
-    if (h->P > 1) {
-        k_beam_solve_reduced<<<(nrhs + 31) / 32, 32, 0, st>>>(h->P, nrhs, h->d_sep, h->Kl, h->RSinv, h->RG, U);
-        const long long t3 = h->N * nrhs;
-        k_beam_solve_fix<<<(unsigned)((t3 + T - 1) / T), T, 0, st>>>(h->N, h->P, nrhs, h->d_sep, d_part, h->Vl, h->Vr, U);
+    double* lo = U_lo;
+    if (h->prec == BFE2_BEAM_DD && !lo) {
+        const int rc = beam_lo_workspace(h, nrhs);
+        if (rc) return rc;
+        lo = h->lo_ws;
     }
-    BEAM_CUDA(cudaGetLastError());
+    if (h->prec != BFE2_BEAM_DD) lo = nullptr;
+    const long long count = h->n * (long long)nrhs;
+    k_beam_load_rhs<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, F, F_lo, U, lo);
+    const int rc = h->prec == BFE2_BEAM_DD ? beam_solve<dd>(h, nrhs, U, lo, st) : beam_solve<double>(h, nrhs, U, nullptr, st);
+    if (rc) return rc;
+    if (h->prec != BFE2_BEAM_DD && U_lo) BEAM_CUDA(cudaMemsetAsync(U_lo, 0, (size_t)count * sizeof(double), st));
     return 0;
+}
+
+int bfe2_beam_solve(bfe2_beam* h, int32_t nrhs, const double* F, double* U, void* stream) {
+    return bfe2_beam_solve_dd(h, nrhs, F, nullptr, U, nullptr, stream);
 }
 
 int bfe2_beam_matvec(bfe2_beam* h, int32_t which, int32_t nrhs, const double* X, double* Y, void* stream) {
     if (!h || nrhs < 1 || !X || !Y || X == Y || which < 0 || which > 1) return bfe2_fail(-1, "bfe2_beam_matvec: bad argument");
-    const int T = 128;
-    const long long t = h->N * nrhs;
-    k_beam_matvec<<<(unsigned)((t + T - 1) / T), T, 0, (cudaStream_t)stream>>>(h->N, nrhs, which ? h->Md : h->Kd,
-                                                                              which ? h->Ml : h->Kl, X, Y);
+    return h->prec == BFE2_BEAM_DD ? beam_matvec<dd>(h, which, nrhs, X, nullptr, nullptr, Y, (cudaStream_t)stream)
+                                   : beam_matvec<double>(h, which, nrhs, X, nullptr, nullptr, Y, (cudaStream_t)stream);
+}
+
+int bfe2_beam_residual(bfe2_beam* h, int32_t nrhs, const double* F, const double* U, const double* U_lo, double* R,
+                       void* stream) {
+    if (!h || nrhs < 1 || !F || !U || !R || R == U || R == U_lo) return bfe2_fail(-1, "bfe2_beam_residual: bad argument");
+    return h->prec == BFE2_BEAM_DD ? beam_matvec<dd>(h, 0, nrhs, U, U_lo, F, R, (cudaStream_t)stream)
+                                   : beam_matvec<double>(h, 0, nrhs, U, nullptr, F, R, (cudaStream_t)stream);
+}
+
+int bfe2_beam_export_blocks(bfe2_beam* h, int32_t which, double* out, void* stream) {
+    if (!h || !out || which < 0 || which > 1) return bfe2_fail(-1, "bfe2_beam_export_blocks: bad argument");
+    const long long t = h->N * 18;
+    const unsigned g = (unsigned)((t + 255) / 256);
+    if (h->prec == BFE2_BEAM_DD)
+        k_beam_export<dd><<<g, 256, 0, (cudaStream_t)stream>>>(h->N, (const dd*)(which ? h->Md : h->Kd),
+                                                              (const dd*)(which ? h->Ml : h->Kl), out);
+    else
+        k_beam_export<double><<<g, 256, 0, (cudaStream_t)stream>>>(h->N, (const double*)(which ? h->Md : h->Kd),
+                                                                  (const double*)(which ? h->Ml : h->Kl), out);
     BEAM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -18,7 +18,9 @@
  *        k>0  non-positive Cholesky pivot of the condensed K at column k (1-based)
  *             == the reference's "stiffness matrix is singular" (Structure.py:325-354)
  *        -1  condensed mass matrix not positive definite / all-zero (Solver.py:34-35 returns False)
- *        -2  Jacobi did not converge in BFE2_MAX_SWEEPS sweeps
+ *        -2  Jacobi did not converge in BFE2_MAX_SWEEPS sweeps / the reduced matrix broke down
+ *     k > 0 invalidates every output of that structure (NaN).  -1 / -2 invalidate only the MODAL outputs
+ *     (lam, phi = NaN): K factored fine, so u / endforces / reactions of that structure are valid.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with -100.
  *
  * Layout of the per-variant tensors (B = number of structure variants sharing one topology plan,
@@ -148,16 +150,34 @@ int bfe2_sym_eig_dense(bfe2_plan* dense_plan, int64_t Bt, const double* A, const
  *      coords [n_elem+1, 2], props [n_elem, 4] are DEVICE pointers, fixed_mask [3 (n_elem+1)] a HOST
  *      pointer (1 = supported DOF, Structure.py:164-181).  The handle owns the block-tridiagonal K, M and
  *      the partitioned Cholesky factor of K (device memory, freed by bfe2_beam_destroy).
- *      Multi-vectors are [n_dof, nrhs] row-major (the nrhs values of a DOF are contiguous). ------------ */
+ *      Multi-vectors are [n_dof, nrhs] row-major (the nrhs values of a DOF are contiguous).
+ *      Precision: cond(K) ~ 16 n^4 (1.6e21 at n = 1e5), so the element matrices, the factorisation and the
+ *      substitutions run in double-double (BFE2_BEAM_DD, the default of bfe2_beam_create; the inputs are exact
+ *      FP64 numbers, eps * cond stays ~2e-11); BFE2_BEAM_FP64 instantiates the same kernels in plain FP64. ---- */
 typedef struct bfe2_beam bfe2_beam;
+#define BFE2_BEAM_FP64 0
+#define BFE2_BEAM_DD   1
 int  bfe2_beam_create(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
                       const uint8_t* fixed_mask, int32_t n_partitions /*0 = auto*/, void* stream);
+int  bfe2_beam_create_ex(bfe2_beam** out, int64_t n_elem, const double* coords, const double* props,
+                         const uint8_t* fixed_mask, int32_t n_partitions /*0 = auto*/, int32_t precision,
+                         void* stream);
 void bfe2_beam_destroy(bfe2_beam* beam);
 int  bfe2_beam_dims(const bfe2_beam* beam, int64_t* n_nodes, int64_t* n_dof, int32_t* n_partitions);
 /* U = K^-1 F (Solver.py:76-87 on the condensed system; supported DOFs come out 0 when F is 0 there) */
 int  bfe2_beam_solve(bfe2_beam* beam, int32_t nrhs, const double* F, double* U, void* stream);
-/* Y = K X (which = 0) or Y = M X (which = 1) */
+/* the same with the low words of the double-double right-hand side / solution exposed: F + F_lo in (F_lo may be
+ * NULL), U + U_lo out (U_lo may be NULL; all zero for a BFE2_BEAM_FP64 handle) */
+int  bfe2_beam_solve_dd(bfe2_beam* beam, int32_t nrhs, const double* F, const double* F_lo /*or NULL*/,
+                        double* U, double* U_lo /*or NULL*/, void* stream);
+/* Y = K X (which = 0) or Y = M X (which = 1); accumulated in the handle's precision, rounded once */
 int  bfe2_beam_matvec(bfe2_beam* beam, int32_t which, int32_t nrhs, const double* X, double* Y, void* stream);
+/* R = F - K (U + U_lo), evaluated in the handle's precision and rounded once (U_lo may be NULL) */
+int  bfe2_beam_residual(bfe2_beam* beam, int32_t nrhs, const double* F, const double* U,
+                        const double* U_lo /*or NULL*/, double* R, void* stream);
+/* introspection: the stored K (which = 0) or M (1) rounded to FP64, out [n_nodes, 2, 3, 3] = diagonal block
+ * (k, k) and sub-diagonal block (k+1, k) of every node */
+int  bfe2_beam_export_blocks(bfe2_beam* beam, int32_t which, double* out, void* stream);
 /* FP64 tensor-core (DMMA) contractions for blocks of exactly 64 vectors:
  *   C [64,64] = X^T Y  for X, Y [n, 64];   Xout [n,64] = Z [n,64] * Q [64,64] */
 size_t bfe2_gram_workspace_bytes(int64_t n);

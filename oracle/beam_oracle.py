@@ -69,3 +69,26 @@ def cantilever_closed_form(P, L, E, I, rho, A, n_modes):
     bl += [(2 * k - 1) * np.pi / 2 for k in range(6, n_modes + 1)]
     w = np.array(bl[:n_modes]) ** 2 * np.sqrt(E * I / (rho * A * L ** 4))
     return P * L ** 3 / (3 * E * I), P * L ** 2 / (2 * E * I), w
+
+
+def cantilever_beta_l(k):
+    """k-th root of cos(x) cosh(x) = -1 (clamped-free Euler-Bernoulli beam), Newton on cos(x) + 1/cosh(x)."""
+    x = (2 * k - 1) * np.pi / 2
+    if k == 1:
+        x = 1.875
+    for _ in range(50):
+        g = np.cos(x) + 1.0 / np.cosh(x)
+        dg = -np.sin(x) - np.sinh(x) / np.cosh(x) ** 2
+        dx = g / dg
+        x -= dx
+        if abs(dx) < 1e-16 * x:
+            break
+    return float(x)
+
+
+def cantilever_spectrum(L, E, I, rho, A, n_modes):
+    """The n_modes lowest circular frequencies of the continuous clamped-free member in the plane: the union of the
+    bending family (beta_k L)^2 sqrt(EI / rho A L^4) and the axial family (2k-1) pi/2 sqrt(E/rho) / L, sorted."""
+    bend = np.array([cantilever_beta_l(k) for k in range(1, n_modes + 1)]) ** 2 * np.sqrt(E * I / (rho * A * L ** 4))
+    axial = (2 * np.arange(1, n_modes + 1) - 1) * np.pi / 2 * np.sqrt(E / rho) / L
+    return np.sort(np.concatenate([bend, axial]))[:n_modes]

@@ -318,6 +318,10 @@ def test_failure_reporting_and_edge_cases():
     keepers = [b for b in range(8) if b != 3]
     assert torch.equal(out['lam'][keepers], good['lam'][keepers])
     assert torch.equal(out['u'][keepers], good['u'][keepers])
+    # the massless variant still has a valid STATIC result (K factored fine): only lam / phi are NaN
+    assert torch.isnan(out['lam'][3]).all() and torch.isnan(out['phi'][3]).all()
+    assert torch.equal(out['u'][3], good['u'][3]) and torch.equal(out['endforces'][3], good['endforces'][3])
+    assert torch.equal(out['reactions'][3], good['reactions'][3])
     # (d) empty batch and wrong shapes
     e = batch.solve_fused(plan, pk['coords'][:0], pk['props'][:0], None, None, None, n_modes=0)
     assert e['lam'].shape == (0, 57)

@@ -26,6 +26,8 @@ def main():
     ap.add_argument('--modes', type=int, default=50)
     ap.add_argument('--cpu-modes', type=int, default=10)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--precision', default='dd', choices=['dd', 'fp64'])
+    ap.add_argument('--partitions', type=int, default=0)
     args = ap.parse_args()
     dev = 'cuda:0'
     n, L = args.n, 1000.0
@@ -33,11 +35,12 @@ def main():
     coords, props = pk['coords'][0], pk['props'][0]
     E, A, I, rho = props[0].cpu().numpy()
     d_cf, r_cf, w_cf = bo.cantilever_closed_form(100.0, L, E, I, rho, A, 8)
-    out = {'n_elem': n, 'n_dof': 3 * (n + 1), 'cond_estimate': 16.0 * n ** 4}
+    spectrum = bo.cantilever_spectrum(L, E, I, rho, A, args.modes)
+    out = {'n_elem': n, 'n_dof': 3 * (n + 1), 'cond_estimate': 16.0 * n ** 4, 'precision': args.precision}
 
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    beam = LargeBeam(coords, props, [0, 1, 2])
+    beam = LargeBeam(coords, props, [0, 1, 2], n_partitions=args.partitions, precision=args.precision)
     torch.cuda.synchronize()
     out['gpu_assemble_factor_ms'] = 1e3 * (time.perf_counter() - t0)
     out['partitions'] = beam.n_partitions
@@ -50,12 +53,16 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     out['gpu_static_solve_ms'] = e0.elapsed_time(e1) / 10
-    r = beam.matvec(u) - f
+    u, ulo = beam.static(f, with_lo=True)
+    r = beam.residual(f, u)                              # u rounded to FP64
+    rdd = beam.residual(f, u, ulo)                       # the full double-double solution
     kmax = float(beam.matvec(torch.ones_like(u)).abs().max().item())
     un = u.cpu().numpy()
+    sc = kmax * float(u.abs().max().item())
     out['gpu_static'] = {'tip_uy': float(un[-2]), 'closed_form': d_cf, 'rel_err_tip': abs(un[-2] / d_cf - 1),
                          'rel_err_rot': abs(un[-1] / r_cf - 1),
-                         'scaled_residual': float(r.abs().max().item()) / (kmax * float(u.abs().max().item()))}
+                         'scaled_residual': float(r.abs().max().item()) / sc,
+                         'scaled_residual_double_double_solution': float(rdd.abs().max().item()) / sc}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     mo = beam.modal(n_modes=args.modes, tol=1e-10, maxit=60)
@@ -67,6 +74,7 @@ def main():
                         'noise_floor': mo['noise_floor'], 'failed': mo['failed'], 'omega_first5_bending': bend.tolist(),
                         'closed_form': w_cf[:5].tolist(),
                         'rel_err_first5': np.abs(bend / w_cf[:len(bend)] - 1).tolist(),
+                        'max_rel_err_all_modes_vs_continuous_member': float(np.abs(om / spectrum - 1).max()) if len(om) == len(spectrum) else None,
                         'max_scaled_residual': float(np.nan_to_num(mo['residual'].cpu().numpy(), nan=-1.0).max())}
     if not args.no_cpu:
         cn, pn = coords.cpu().numpy(), props.cpu().numpy()
