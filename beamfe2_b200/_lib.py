@@ -15,6 +15,7 @@ SYMBOLS = (
     'bfe2_plan_smem_bytes', 'bfe2_workspace_bytes',
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
     'bfe2_solve_fused',
+    'bfe2_pattern_create', 'bfe2_pattern_destroy', 'bfe2_pattern_layout', 'bfe2_solve_fused_packed',
     'bfe2_plan_create_dense', 'bfe2_sym_eig_dense',
     'bfe2_beam_create', 'bfe2_beam_create_ex', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve',
     'bfe2_beam_solve_dd', 'bfe2_beam_matvec', 'bfe2_beam_residual', 'bfe2_beam_export_blocks',
@@ -81,6 +82,14 @@ def lib():
     L.bfe2_modal_solve.argtypes = [vp, i64, i32] + [vp] * 7
     L.bfe2_solve_fused.restype = C.c_int
     L.bfe2_solve_fused.argtypes = [vp, i64, i32, i32, i32] + [vp] * 13
+    L.bfe2_pattern_create.restype = C.c_int
+    L.bfe2_pattern_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32, i32, vp, i32, vp]
+    L.bfe2_pattern_destroy.restype = None
+    L.bfe2_pattern_destroy.argtypes = [vp]
+    L.bfe2_pattern_layout.restype = C.c_int
+    L.bfe2_pattern_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp]
+    L.bfe2_solve_fused_packed.restype = C.c_int
+    L.bfe2_solve_fused_packed.argtypes = [vp, vp, i64, vp, vp, vp]
     L.bfe2_plan_create_dense.restype = C.c_int
     L.bfe2_plan_create_dense.argtypes = [C.POINTER(vp), i32]
     L.bfe2_sym_eig_dense.restype = C.c_int

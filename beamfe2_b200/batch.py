@@ -170,54 +170,168 @@ def modal_participation(plan: Plan, Mb, phi):
     return gamma
 
 
-class HostPipeline:
-    """End-to-end path with HOST buffers: pinned host tensors -> H2D -> fused kernel -> D2H, chunked
-    over a few CUDA streams so that copies overlap the kernels.  This is the call a user of the
-    reference-facing API makes when the model data lives on the host (the reference keeps everything
-    in host numpy matrices, BeamFE2/Structure.py)."""
+class PackedIO:
+    """Packed per-structure records with compact load / result layouts (include/bfe2.h: bfe2_pattern_*).
 
-    IN_KEYS = ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')
-    OUT_KEYS = ('u', 'endforces', 'reactions', 'lam', 'phi', 'info', 'sweeps')
+    f_index / r_index: the dense indices (into [C, sumdof] and [C, nE, 6]) of the load entries that may be non-zero
+    anywhere in the batch -- the reference's add_nodal_load / add_internal_loads touch a handful of positions
+    (Structure.py:244-287).  `PackedIO.from_dense` derives them from example tensors.  None = every entry."""
 
-    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, chunk: int = 4096, n_streams: int = 3,
-                 device=None, modal: bool = True):
+    IN_FIELDS = ('coords', 'props', 'nodal_mass', 'f_values', 'r_values')
+    OUT_FIELDS = ('u', 'endforces', 'reactions', 'lam', 'phi', 'status')
+
+    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, modal: bool = True, f_index=None, r_index=None):
+        import ctypes as C
+        import numpy as np
         self.plan, self.C, self.modal = plan, int(n_loadcases), bool(modal)
         self.n_modes = int(n_modes) if modal else 0
+        nf, nr = self.C * plan.sumdof, self.C * plan.n_elem * 6
+        self.f_index = np.arange(nf, dtype=np.int32) if f_index is None else np.ascontiguousarray(f_index, dtype=np.int32)
+        self.r_index = np.arange(nr, dtype=np.int32) if r_index is None else np.ascontiguousarray(r_index, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bfe2_pattern_create(C.byref(h), plan.handle, self.C, 1 if modal else 0, self.n_modes,
+                                                  int(self.f_index.size), _lib.ptr(self.f_index) if self.f_index.size else None,
+                                                  int(self.r_index.size), _lib.ptr(self.r_index) if self.r_index.size else None))
+        self._h = h
+        wi, wo = C.c_int32(), C.c_int32()
+        oi, oo = (C.c_int32 * 5)(), (C.c_int32 * 6)()
+        _lib.check(_lib.lib().bfe2_pattern_layout(h, C.byref(wi), C.byref(wo), oi, oo))
+        self.w_in, self.w_out = wi.value, wo.value
+        self.in_off, self.out_off = list(oi), list(oo)
+        p, Cn, n = plan, self.C, plan.n_free
+        self.n_fixed = int(plan.fixed.size)
+        self.in_shapes = dict(coords=(p.n_nodes, 2), props=(p.n_elem, 4), nodal_mass=(p.n_nodes, 2),
+                              f_values=(int(self.f_index.size),), r_values=(int(self.r_index.size),))
+        self.out_shapes = dict(u=(Cn, n), endforces=(Cn, p.n_elem, 6), reactions=(Cn, self.n_fixed),
+                               lam=(n if modal else 0,), phi=(self.n_modes, n), status=(1,))
+
+    @classmethod
+    def from_dense(cls, plan, f_nodal, r_local, n_modes, modal=True):
+        """Load pattern = union over the batch of the non-zero entries of example dense tensors
+        f_nodal [B, C, sumdof], r_local [B, C, nE, 6] (either may be None)."""
+        import numpy as np
+        C = 0 if f_nodal is None else int(f_nodal.shape[1])
+        fi = np.zeros(0, dtype=np.int32)
+        ri = np.zeros(0, dtype=np.int32)
+        if f_nodal is not None:
+            fi = torch.nonzero((f_nodal != 0).any(dim=0).reshape(-1)).reshape(-1).cpu().numpy().astype(np.int32)
+        if r_local is not None:
+            ri = torch.nonzero((r_local != 0).any(dim=0).reshape(-1)).reshape(-1).cpu().numpy().astype(np.int32)
+        return cls(plan, C, n_modes, modal, fi, ri)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.lib().bfe2_pattern_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- views into records ([B, w] tensors on any device) -------------------------------------
+    def _views(self, rec, offs, shapes, names):
+        import math
+        out = {}
+        for name, o in zip(names, offs):
+            shp = shapes[name]
+            k = math.prod(shp)
+            out[name] = rec[:, o:o + k].unflatten(1, shp) if k else rec[:, o:o].reshape((rec.shape[0],) + tuple(shp))
+        return out
+
+    def in_views(self, rec):
+        return self._views(rec, self.in_off, self.in_shapes, self.IN_FIELDS)
+
+    def out_views(self, rec):
+        v = self._views(rec, self.out_off, self.out_shapes, self.OUT_FIELDS)
+        v.pop('status')                                    # one float64 slot holding two int32: info, sweeps
+        ints = rec.view(torch.int32)                       # [B, 2 w_out]
+        v['info'], v['sweeps'] = ints[:, 2 * self.out_off[5]], ints[:, 2 * self.out_off[5] + 1]
+        return v
+
+    def pack_inputs(self, rec, coords, props, nodal_mass=None, f_nodal=None, r_local=None):
+        """Fill the input records from dense tensors (gathers the load entries of the pattern)."""
+        v = self.in_views(rec)
+        v['coords'].copy_(coords)
+        v['props'].copy_(props)
+        if nodal_mass is None:
+            v['nodal_mass'].zero_()
+        else:
+            v['nodal_mass'].copy_(nodal_mass)
+        B = rec.shape[0]
+        if self.f_index.size:
+            idx = torch.as_tensor(self.f_index, dtype=torch.long, device=f_nodal.device)
+            v['f_values'].copy_(f_nodal.reshape(B, -1)[:, idx])
+        if self.r_index.size:
+            idx = torch.as_tensor(self.r_index, dtype=torch.long, device=r_local.device)
+            v['r_values'].copy_(r_local.reshape(B, -1)[:, idx])
+        return rec
+
+    def expand(self, views):
+        """Compact results -> the dense layouts of solve_fused: u / phi on all DOFs (zeros at supports), reactions
+        on all DOFs (NaN-free zeros away from the supports).  Works on host or device tensors."""
+        pos = torch.as_tensor(self.plan.pos_of_free.astype('int64'), device=views['info'].device)
+        fixed = torch.as_tensor(self.plan.fixed.astype('int64'), device=views['info'].device)
+        B, sd = views['info'].shape[0], self.plan.sumdof
+        out = dict(endforces=views['endforces'], lam=views['lam'], info=views['info'], sweeps=views['sweeps'])
+        if self.C > 0:
+            u = torch.zeros((B, self.C, sd), dtype=torch.float64, device=pos.device)
+            u[:, :, pos] = views['u']
+            re = torch.zeros((B, self.C, sd), dtype=torch.float64, device=pos.device)
+            re[:, :, fixed] = views['reactions']
+            out.update(u=u, reactions=re)
+        if self.n_modes > 0:
+            phi = torch.zeros((B, self.n_modes, sd), dtype=torch.float64, device=pos.device)
+            phi[:, :, pos] = views['phi']
+            out['phi'] = phi
+        return out
+
+    def solve(self, in_rec, out_rec=None):
+        """Run the fused kernel on device records in_rec [B, w_in] -> out_rec [B, w_out]."""
+        B = in_rec.shape[0]
+        in_rec = _chk(in_rec, (B, self.w_in), 'in_rec')
+        if out_rec is None:
+            out_rec = torch.empty((B, self.w_out), dtype=torch.float64, device=in_rec.device)
+        elif not out_rec.is_contiguous():
+            raise ValueError('out_rec must be contiguous')
+        out_rec = _chk(out_rec, (B, self.w_out), 'out_rec')
+        with torch.cuda.device(in_rec.device):
+            _lib.check(_lib.lib().bfe2_solve_fused_packed(self.plan.handle, self._h, B, _lib.ptr(in_rec),
+                                                          _lib.ptr(out_rec), _stream_ptr()))
+        return out_rec
+
+
+class HostPipeline:
+    """End-to-end path with HOST buffers: pinned host records -> H2D -> fused kernel -> D2H, chunked over a few
+    CUDA streams so that copies overlap the kernels.  This is the call a user of the reference-facing API makes
+    when the model data lives on the host (the reference keeps everything in host numpy matrices,
+    BeamFE2/Structure.py).  One packed record per structure and direction (PackedIO): ONE cudaMemcpyAsync each way
+    per chunk, and only the non-zero load entries, the free-DOF displacements / shapes and the support reactions
+    cross the bus (P20: 1.7 KB in + 9.4 KB out per structure instead of 5.7 + 11.4 KB dense)."""
+
+    def __init__(self, plan: Plan, n_loadcases: int, n_modes: int, chunk: int = 4096, n_streams: int = 3,
+                 device=None, modal: bool = True, f_index=None, r_index=None, io: PackedIO = None):
+        self.io = io if io is not None else PackedIO(plan, n_loadcases, n_modes, modal, f_index, r_index)
+        self.plan, self.C, self.modal, self.n_modes = plan, self.io.C, self.io.modal, self.io.n_modes
         self.chunk = int(chunk)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        p, C = plan, self.C
-        self.in_shapes = dict(coords=(p.n_nodes, 2), props=(p.n_elem, 4), nodal_mass=(p.n_nodes, 2),
-                              f_nodal=(C, p.sumdof), r_local=(C, p.n_elem, 6))
-        self.out_shapes = dict(u=(C, p.sumdof), endforces=(C, p.n_elem, 6), reactions=(C, p.sumdof),
-                               lam=(p.n_free,), phi=(self.n_modes, p.sumdof), info=(), sweeps=())
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
-        self.stage = []
-        for _ in range(n_streams):
-            d_in = {k: torch.empty((self.chunk,) + s, dtype=torch.float64, device=self.device)
-                    for k, s in self.in_shapes.items()}
-            d_out = {k: torch.empty((self.chunk,) + s, device=self.device,
-                                    dtype=torch.int32 if k in ('info', 'sweeps') else torch.float64)
-                     for k, s in self.out_shapes.items()}
-            self.stage.append((d_in, d_out))
+        self.stage = [(torch.empty((self.chunk, self.io.w_in), dtype=torch.float64, device=self.device),
+                       torch.empty((self.chunk, self.io.w_out), dtype=torch.float64, device=self.device))
+                      for _ in range(n_streams)]
         self.launches = 0
+        self.copies = 0
 
     def alloc_host(self, B: int):
-        """Pinned host input and output buffers for a batch of B."""
-        h_in = {k: torch.empty((B,) + s, dtype=torch.float64).pin_memory() for k, s in self.in_shapes.items()}
-        h_out = {k: torch.empty((B,) + s, dtype=torch.int32 if k in ('info', 'sweeps') else torch.float64).pin_memory()
-                 for k, s in self.out_shapes.items()}
-        return h_in, h_out
+        """Pinned host records for a batch of B: (in_rec [B, w_in], out_rec [B, w_out]).  Field views:
+        self.io.in_views(in_rec) / self.io.out_views(out_rec); dense layouts: self.io.expand(views)."""
+        return (torch.zeros((B, self.io.w_in), dtype=torch.float64).pin_memory(),
+                torch.empty((B, self.io.w_out), dtype=torch.float64).pin_memory())
 
     def bytes_per_structure(self):
-        import math
-        bi = sum(8 * math.prod(s) for s in self.in_shapes.values())
-        bo = sum((4 if k in ('info', 'sweeps') else 8) * math.prod(s) for k, s in self.out_shapes.items())
-        return bi, bo
+        return 8 * self.io.w_in, 8 * self.io.w_out
 
-    def run(self, h_in: dict, h_out: dict):
+    def run(self, h_in, h_out):
         """Enqueue the whole batch; returns after everything has landed in h_out."""
-        B = h_in['coords'].shape[0]
-        use_static = self.C > 0
+        B = h_in.shape[0]
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(cur)
@@ -227,24 +341,11 @@ class HostPipeline:
             st = self.streams[ci % len(self.streams)]
             d_in, d_out = self.stage[ci % len(self.streams)]
             with torch.cuda.stream(st):
-                for k in self.IN_KEYS:
-                    if not use_static and k in ('f_nodal', 'r_local'):
-                        continue
-                    d_in[k][:m].copy_(h_in[k][lo:hi], non_blocking=True)
-                solve_fused(self.plan, d_in['coords'][:m], d_in['props'][:m], d_in['nodal_mass'][:m],
-                            d_in['f_nodal'][:m] if use_static else None,
-                            d_in['r_local'][:m] if use_static else None,
-                            modal=self.modal, n_modes=self.n_modes,
-                            out={k: v[:m] for k, v in d_out.items()})
+                d_in[:m].copy_(h_in[lo:hi], non_blocking=True)
+                self.io.solve(d_in[:m], d_out[:m])
+                h_out[lo:hi].copy_(d_out[:m], non_blocking=True)
                 self.launches += 1
-                for k in self.OUT_KEYS:
-                    if d_out[k].numel() == 0:
-                        continue
-                    if not use_static and k in ('u', 'endforces', 'reactions'):
-                        continue
-                    if not self.modal and k in ('lam', 'phi'):
-                        continue
-                    h_out[k][lo:hi].copy_(d_out[k][:m], non_blocking=True)
+                self.copies += 2
         for s in self.streams:
             cur.wait_stream(s)
         cur.synchronize()

@@ -20,6 +20,13 @@ using namespace bfe2;
 // =================================================================================================
 // error plumbing
 // =================================================================================================
+// This file is compiled twice (Makefile): as itself -- everything except the packed-record entry points -- and, with
+// BFE2_TU_PACKED defined, through bfe2_packed.cu, which keeps only bfe2_pattern_* / bfe2_solve_fused_packed and the
+// PACKED instantiations of k_solve.  Two translation units compile side by side; the kernels are templates in an
+// anonymous namespace, so each unit instantiates only what its entry points launch.
+int bfe2_fail(int code, const char* fmt, ...);
+
+#ifndef BFE2_TU_PACKED
 namespace {
 thread_local std::string g_err = "";
 
@@ -35,7 +42,7 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace
 
-// shared with bfe2_beam.cu
+// shared with bfe2_beam.cu, bfe2_post.cu and bfe2_packed.cu
 int bfe2_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -45,6 +52,9 @@ int bfe2_fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+#else
+#define fail bfe2_fail
+#endif
 
 namespace {
 #define BFE2_CUDA(call)                                                                         \
@@ -185,7 +195,11 @@ int plan_upload(bfe2_plan* p, PlanDev* out) {
 }  // namespace
 
 // shared with bfe2_post.cu: device view of a plan on the current device (uploads lazily); < 0 + last_error on failure
+#ifndef BFE2_TU_PACKED
 int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out) { return plan_upload(plan, out); }
+#else
+int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out);
+#endif
 
 // =================================================================================================
 // kernels
@@ -200,6 +214,12 @@ struct BatchArgs {
     double *Kb_out, *Mb_out;                                         // K2 outputs
     double *u, *endforces, *reactions, *lam, *phi;
     int32_t *info, *sweeps;
+    // packed records (bfe2_solve_fused_packed; k_solve only).  w_in / w_out > 0: every input (output) pointer is the
+    // address of that array inside structure 0's record and consecutive structures are w_in (w_out) doubles apart.
+    // compact_in: f_nodal / r_local hold only the nnz_f / nnz_r values named by f_idx / r_idx (dense indices into
+    // [C, sumdof] and [C, nE, 6]); compact_out: u and phi on the n free DOFs, reactions at the n_fixed supported ones.
+    int w_in, w_out, compact_in, compact_out, nnz_f, nnz_r, n_fixed;
+    const int32_t *f_idx, *r_idx, *fixed_pos;
 };
 
 __device__ __forceinline__ void copy_in(double* dst, const double* src, int count, int tid, int nt) {
@@ -780,7 +800,10 @@ int dispatch_static_group(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
 //   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
 //   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
+//   PACKED = 1: packed records / compact layouts (bfe2_solve_fused_packed); a separate instantiation, so that the
+//   dense kernel carries none of that code (the register-resident sweep loop is sensitive to what ptxas has to
+//   keep around it: with run-time flags the dense P20 launch went from 46.0 to 49.9 ms).
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS, bool PACKED = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_solve(PlanDev P, BatchArgs A) {
     extern __shared__ __align__(16) double smem[];
@@ -791,13 +814,17 @@ k_solve(PlanDev P, BatchArgs A) {
     int* s_order = reinterpret_cast<int*>(smem + L.order);
     int* s_flag = s_order + P.npad;                  // [0] = K cholesky info, [1] = M cholesky info
 
+    // per-structure strides (doubles): natural sizes of the dense tensors, or the record widths when packed.  The
+    // output addresses are formed where they are used (after the sweeps), so nothing extra stays live across them.
+    const long long in_w = PACKED ? A.w_in : 0;
+    const bool compact_out = PACKED && A.compact_out;
     const bool need_geo = ASSEMBLE || A.do_static;
     if (need_geo) {
-        copy_in(smem + L.coords, A.coords + b * 2 * P.nN, 2 * P.nN, tid, nt);
-        copy_in(smem + L.props, A.props + b * 4 * P.nE, 4 * P.nE, tid, nt);
+        copy_in(smem + L.coords, A.coords + b * (in_w ? in_w : 2LL * P.nN), 2 * P.nN, tid, nt);
+        copy_in(smem + L.props, A.props + b * (in_w ? in_w : 4LL * P.nE), 4 * P.nE, tid, nt);
     }
     if (ASSEMBLE && A.do_modal && A.nodal_mass != nullptr)
-        copy_in(smem + L.mass, A.nodal_mass + b * 2 * P.nN, 2 * P.nN, tid, nt);
+        copy_in(smem + L.mass, A.nodal_mass + b * (in_w ? in_w : 2LL * P.nN), 2 * P.nN, tid, nt);
     if (!ASSEMBLE) {
         copy_in(smem + L.Kb, A.Kb_in + b * P.nslots, P.nslots, tid, nt);
         if (A.do_modal) copy_in(smem + L.Mb, A.Mb_in + b * P.nslots, P.nslots, tid, nt);
@@ -836,31 +863,67 @@ k_solve(PlanDev P, BatchArgs A) {
         }
         __syncthreads();
     };
+    struct Outs {
+        double *u, *ef, *re, *lam, *phi;
+        int32_t *info, *sweeps;
+        int nu, nre;
+    };
+    auto outs = [&]() {
+        Outs o;
+        const long long out_w = PACKED ? A.w_out : 0;
+        o.nu = compact_out ? n : P.sumdof;           // u / phi entries per load case / mode
+        o.nre = compact_out ? A.n_fixed : P.sumdof;
+        o.u = A.u ? A.u + b * (out_w ? out_w : (long long)A.C * o.nu) : nullptr;
+        o.ef = A.endforces ? A.endforces + b * (out_w ? out_w : (long long)A.C * P.nE * 6) : nullptr;
+        o.re = A.reactions ? A.reactions + b * (out_w ? out_w : (long long)A.C * o.nre) : nullptr;
+        o.lam = A.lam ? A.lam + b * (out_w ? out_w : (long long)n) : nullptr;
+        o.phi = A.phi ? A.phi + b * (out_w ? out_w : (long long)A.n_modes * o.nu) : nullptr;
+        o.info = A.info + b * (out_w ? 2 * out_w : 1);
+        o.sweeps = A.sweeps ? A.sweeps + b * (out_w ? 2 * out_w : 1) : nullptr;
+        return o;
+    };
+    auto fail_modal = [&](const Outs& o) {
+        fill_nan(o.lam, n, tid, nt);
+        fill_nan(o.phi, (long long)A.n_modes * o.nu, tid, nt);
+    };
     auto fail_all = [&](int code) {                  // numerical failure: NaN outputs, per-structure info
+        const Outs o = outs();
         if (tid == 0) {
-            A.info[b] = code;
-            if (A.sweeps) A.sweeps[b] = 0;
+            *o.info = code;
+            if (o.sweeps) *o.sweeps = 0;
         }
         if (A.do_static) {
-            fill_nan(A.u ? A.u + b * A.C * P.sumdof : nullptr, (long long)A.C * P.sumdof, tid, nt);
-            fill_nan(A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr, (long long)A.C * P.nE * 6, tid, nt);
-            fill_nan(A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, (long long)A.C * P.sumdof, tid, nt);
+            fill_nan(o.u, (long long)A.C * o.nu, tid, nt);
+            fill_nan(o.ef, (long long)A.C * P.nE * 6, tid, nt);
+            fill_nan(o.re, (long long)A.C * o.nre, tid, nt);
         }
-        if (A.do_modal) {
-            fill_nan(A.lam + b * n, n, tid, nt);
-            fill_nan(A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, (long long)A.n_modes * P.sumdof, tid, nt);
-        }
+        if (A.do_modal) fail_modal(o);
     };
     auto static_stage = [&]() {
         double* s_f = smem + L.U;
         double* s_ufull = s_f + A.C * n;
         double* s_ef = s_ufull + A.C * P.sumdof;
+        const Outs o = outs();
+        const double* g_fnod = A.f_nodal ? A.f_nodal + b * (in_w ? in_w : (long long)A.C * P.sumdof) : nullptr;
+        const double* g_rloc = A.r_local ? A.r_local + b * (in_w ? in_w : (long long)A.C * P.nE * 6) : nullptr;
+        const double* fn = g_fnod;
+        const double* rl = g_rloc;
+        if (PACKED && A.compact_in) {
+            // compact loads: expand the nnz values of the load pattern into dense [C, sumdof] / [C, nE, 6] arrays in
+            // shared memory (the modal stage is over: region U is free), then run the dense stage on them
+            double* s_fd = s_ef + A.C * P.nE * 6;
+            double* s_rd = s_fd + A.C * P.sumdof;
+            const int nd = A.C * (P.sumdof + 6 * P.nE);
+            for (int i = tid; i < nd; i += nt) s_fd[i] = 0.0;
+            __syncthreads();
+            for (int i = tid; i < A.nnz_f; i += nt) s_fd[A.f_idx[i]] = g_fnod[i];
+            for (int i = tid; i < A.nnz_r; i += nt) s_rd[A.r_idx[i]] = g_rloc[i];
+            __syncthreads();
+            fn = s_fd;
+            rl = A.nnz_r > 0 ? s_rd : nullptr;
+        }
         stage_static(P, A.C, smem + L.props, smem + L.geo, smem + L.Kb, smem + L.invK, s_f, s_ufull, s_ef,
-                     A.f_nodal + b * A.C * P.sumdof,
-                     A.r_local ? A.r_local + b * A.C * P.nE * 6 : nullptr,
-                     A.u + b * A.C * P.sumdof,
-                     A.endforces ? A.endforces + b * A.C * P.nE * 6 : nullptr,
-                     A.reactions ? A.reactions + b * A.C * P.sumdof : nullptr, tid, nt, ASSEMBLE);
+                     fn, rl, o.u, o.ef, o.re, tid, nt, ASSEMBLE, compact_out ? A.fixed_pos : nullptr, A.n_fixed);
     };
     int info = 0;
     {
@@ -895,9 +958,9 @@ k_solve(PlanDev P, BatchArgs A) {
                              ? stage_jacobi_oe<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid) : INT_MIN;
                 }
                 if (sw != INT_MIN) {
+                    const Outs o = outs();
                     stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
-                                            A.lam + b * n, A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr,
-                                            tid, nt, ASSEMBLE);
+                                            o.lam, o.phi, tid, nt, ASSEMBLE, compact_out);
                 }
                 __syncthreads();
             }
@@ -911,29 +974,29 @@ k_solve(PlanDev P, BatchArgs A) {
         if (infoM != 0 || sw == INT_MIN) {
             // the mass matrix is not positive definite (-1) or the pivoted Cholesky broke down (-2): only the MODAL
             // outputs are invalid -- K factored fine, so the static results of this structure are still delivered
+            const Outs o = outs();
             if (tid == 0) {
-                A.info[b] = infoM != 0 ? -1 : -2;
-                if (A.sweeps) A.sweeps[b] = 0;
+                *o.info = infoM != 0 ? -1 : -2;
+                if (o.sweeps) *o.sweeps = 0;
             }
-            fill_nan(A.lam + b * n, n, tid, nt);
-            fill_nan(A.phi ? A.phi + b * A.n_modes * P.sumdof : nullptr, (long long)A.n_modes * P.sumdof, tid, nt);
+            fail_modal(o);
             if (A.do_static) static_stage();
             return;
         }
         if (sw < 0) info = -2;
-        if (tid == 0 && A.sweeps) A.sweeps[b] = sw < 0 ? -sw : sw;
+        if (tid == 0 && A.sweeps) *outs().sweeps = sw < 0 ? -sw : sw;
         if (A.do_static) static_stage();
     }
-    if (tid == 0) A.info[b] = info;
+    if (tid == 0) *outs().info = info;
 }
 
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS>
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS, bool PACKED = false>
 int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
     PlanDev P = pd;
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
-    auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE, REGS>;
+    auto kern = k_solve<RPL, LPP, NT, MINB, ASSEMBLE, REGS, PACKED>;
     BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     if (A.B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
     kern<<<(unsigned)A.B, NT, bytes, stream>>>(P, A);
@@ -1020,22 +1083,22 @@ int launch_static_global(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A,
     return 0;
 }
 
-template <bool ASSEMBLE>
+template <bool ASSEMBLE, bool PACKED = false>
 int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     // n <= 64: register-resident, preconditioned odd-even Jacobi (two warps per structure);
     // 64 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
     if (plan->lpp == 2) {
-        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
-        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true>(plan, pd, A, stream);
+        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
         // __launch_bounds__(64, 5): same 168 registers and 6 resident blocks as (64, 6), but ptxas schedules the
         // software-pipelined step better (+4.7 % measured); (64, 4) takes 216 registers, 4 blocks and is slower.
-        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
-        if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true>(plan, pd, A, stream);
+        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
     }
-    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 3, ASSEMBLE, false>(plan, pd, A, stream);
-    if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, false>(plan, pd, A, stream);
-    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 2, ASSEMBLE, false>(plan, pd, A, stream);
-    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false>(plan, pd, A, stream);
+    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 3, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 2, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
 
@@ -1046,6 +1109,7 @@ int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaS
 // =================================================================================================
 extern "C" {
 
+#ifndef BFE2_TU_PACKED
 int bfe2_version(void) { return BFE2_VERSION; }
 
 const char* bfe2_last_error(void) { return g_err.c_str(); }
@@ -1358,7 +1422,140 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
     return dispatch_solve<true>(plan, pd, A, (cudaStream_t)stream);
 }
 
+#endif  // !BFE2_TU_PACKED
 
+#ifdef BFE2_TU_PACKED
+// ---- packed records + compact load / result layouts (end-to-end path from HOST memory) -----------------
+// One record per structure and direction, so that a chunk of the batch moves with ONE copy each way, and only the
+// numbers that carry information travel: the non-zero entries of the load tensors (a load pattern shared by the
+// batch -- the reference's add_nodal_load / add_internal_loads touch a handful of positions, Structure.py:258-287),
+// displacements and shapes on the free DOFs (the reference re-inserts the zero rows on the host, Solver.py:57-65),
+// reactions at the supported DOFs (the only ones Results.py:129-143 reads).
+struct bfe2_pattern {
+    int C = 0, do_modal = 0, n_modes = 0, nnz_f = 0, nnz_r = 0, n_fixed = 0;
+    int in_off[5] = {0, 0, 0, 0, 0}, out_off[7] = {0, 0, 0, 0, 0, 0, 0};
+    int w_in = 0, w_out = 0;
+    std::vector<int32_t> host;                        // f_idx | r_idx | fixed_pos
+    std::mutex mu;
+    std::map<int, int32_t*> copies;                   // device mirrors, one per device
+    ~bfe2_pattern() {
+        for (auto& kv : copies) cudaFree(kv.second);
+    }
+};
+
+int bfe2_pattern_create(bfe2_pattern** out, bfe2_plan* plan, int32_t C, int32_t do_modal, int32_t n_modes,
+                        int32_t nnz_f, const int32_t* f_index, int32_t nnz_r, const int32_t* r_index) {
+    if (!out || !plan || C < 0 || nnz_f < 0 || nnz_r < 0 || (nnz_f > 0 && !f_index) || (nnz_r > 0 && !r_index))
+        return fail(-1, "bfe2_pattern_create: bad argument");
+    if (C == 0 && !do_modal) return fail(-1, "bfe2_pattern_create: nothing to do");
+    if (do_modal && (n_modes < 0 || n_modes > plan->n)) return fail(-1, "bfe2_pattern_create: bad n_modes");
+    if (do_modal && plan->rpl == 0)
+        return fail(-3, "n_free = %d is outside the Jacobi path (1..%d)", plan->n, BFE2_MAX_JACOBI_N);
+    for (int i = 0; i < nnz_f; ++i)
+        if (f_index[i] < 0 || f_index[i] >= C * plan->sumdof) return fail(-1, "bfe2_pattern_create: f_index[%d] out of range", i);
+    for (int i = 0; i < nnz_r; ++i)
+        if (r_index[i] < 0 || r_index[i] >= C * plan->nE * 6) return fail(-1, "bfe2_pattern_create: r_index[%d] out of range", i);
+    bfe2_pattern* q = new bfe2_pattern();
+    q->C = C; q->do_modal = do_modal != 0; q->n_modes = do_modal ? n_modes : 0;
+    q->nnz_f = nnz_f; q->nnz_r = nnz_r; q->n_fixed = (int)plan->fixed.size();
+    q->host.insert(q->host.end(), f_index, f_index + nnz_f);
+    q->host.insert(q->host.end(), r_index, r_index + nnz_r);
+    q->host.insert(q->host.end(), plan->fixed.begin(), plan->fixed.end());
+    // input record: coords | props | nodal_mass | f values | r values
+    int o = 0;
+    q->in_off[0] = o; o += 2 * plan->nN;
+    q->in_off[1] = o; o += 4 * plan->nE;
+    q->in_off[2] = o; o += 2 * plan->nN;
+    q->in_off[3] = o; o += nnz_f;
+    q->in_off[4] = o; o += nnz_r;
+    q->w_in = o;
+    // output record: u [C, n] | endforces [C, nE, 6] | reactions [C, n_fixed] | lam [n] | phi [n_modes, n] | info, sweeps
+    o = 0;
+    q->out_off[0] = o; o += C * plan->n;
+    q->out_off[1] = o; o += C * plan->nE * 6;
+    q->out_off[2] = o; o += C * q->n_fixed;
+    q->out_off[3] = o; o += q->do_modal ? plan->n : 0;
+    q->out_off[4] = o; o += q->n_modes * plan->n;
+    q->out_off[5] = o; o += 1;                        // two int32: info, sweeps
+    q->out_off[6] = o;
+    q->w_out = o;
+    *out = q;
+    return 0;
+}
+
+void bfe2_pattern_destroy(bfe2_pattern* q) { delete q; }
+
+int bfe2_pattern_layout(const bfe2_pattern* q, int32_t* in_width, int32_t* out_width, int32_t* in_offsets,
+                        int32_t* out_offsets) {
+    if (!q) return fail(-1, "pattern is NULL");
+    if (in_width) *in_width = q->w_in;
+    if (out_width) *out_width = q->w_out;
+    if (in_offsets) memcpy(in_offsets, q->in_off, sizeof(q->in_off));
+    if (out_offsets) memcpy(out_offsets, q->out_off, 6 * sizeof(int));
+    return 0;
+}
+
+int bfe2_solve_fused_packed(bfe2_plan* plan, bfe2_pattern* q, int64_t B, const double* in_rec, double* out_rec,
+                            void* stream) {
+    if (!plan || !q || B < 0 || (B > 0 && (!in_rec || !out_rec))) return fail(-1, "bfe2_solve_fused_packed: bad argument");
+    if (B == 0) return 0;
+    if (q->n_fixed != (int)plan->fixed.size()) return fail(-1, "pattern was created for another plan");
+    PlanDev pd;
+    if (int r = bfe2_plan_device_view(plan, &pd)) return r;
+    int dev = 0;
+    BFE2_CUDA(cudaGetDevice(&dev));
+    const int32_t* dpat = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(q->mu);
+        auto it = q->copies.find(dev);
+        if (it == q->copies.end()) {
+            int32_t* d = nullptr;
+            const size_t bytes = std::max<size_t>(4, q->host.size() * sizeof(int32_t));
+            BFE2_CUDA(cudaMalloc(&d, bytes));
+            if (!q->host.empty() && cudaMemcpy(d, q->host.data(), q->host.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(d);
+                return fail(-100, "pattern upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            it = q->copies.emplace(dev, d).first;
+        }
+        dpat = it->second;
+    }
+    BatchArgs A{};
+    A.B = B; A.C = q->C; A.do_static = q->C > 0; A.do_modal = q->do_modal; A.n_modes = q->n_modes;
+    A.max_sweeps = BFE2_MAX_SWEEPS;
+    A.w_in = q->w_in; A.w_out = q->w_out; A.compact_in = 1; A.compact_out = 1;
+    A.nnz_f = q->nnz_f; A.nnz_r = q->nnz_r; A.n_fixed = q->n_fixed;
+    A.f_idx = dpat; A.r_idx = dpat + q->nnz_f; A.fixed_pos = dpat + q->nnz_f + q->nnz_r;
+    A.coords = in_rec + q->in_off[0]; A.props = in_rec + q->in_off[1]; A.nodal_mass = in_rec + q->in_off[2];
+    if (q->C > 0) {
+        A.f_nodal = in_rec + q->in_off[3]; A.r_local = in_rec + q->in_off[4];
+        A.u = out_rec + q->out_off[0]; A.endforces = out_rec + q->out_off[1]; A.reactions = out_rec + q->out_off[2];
+    }
+    if (q->do_modal) {
+        A.lam = out_rec + q->out_off[3];
+        A.phi = q->n_modes > 0 ? out_rec + q->out_off[4] : nullptr;
+    }
+    A.info = reinterpret_cast<int32_t*>(out_rec + q->out_off[5]);
+    A.sweeps = A.info + 1;
+    if (!q->do_modal) {                               // static only: the block-per-structure kernel without the modal stage
+        PlanDev P = pd;
+        P.npad = 0; P.LD = 0;
+        const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, q->C);
+        const size_t bytes = (size_t)L.total * sizeof(double);
+        if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
+        auto kern = k_solve<5, 2, 64, 8, true, false, true>;
+        BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
+        kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
+        BFE2_CUDA(cudaGetLastError());
+        return 0;
+    }
+    return dispatch_solve<true, true>(plan, pd, A, (cudaStream_t)stream);
+}
+
+#endif  // BFE2_TU_PACKED
+
+#ifndef BFE2_TU_PACKED
 // ---- small dense generalized symmetric eigenproblem A q = theta B q (Rayleigh-Ritz step of the subspace
 //      iteration): the same Cholesky-reduction + Jacobi kernel on a synthetic "plan" with identity maps ---
 int bfe2_plan_create_dense(bfe2_plan** out, int32_t n) {
@@ -1402,5 +1599,7 @@ int bfe2_sym_eig_dense(bfe2_plan* plan, int64_t B, const double* A, const double
     BFE2_CUDA(cudaGetLastError());
     return bfe2_modal_solve(plan, B, n, workspace, workspace + tot, lam, V, info, sweeps, stream);
 }
+
+#endif  // !BFE2_TU_PACKED
 
 }  // extern "C"

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -338,8 +339,10 @@ int bfe2_beam_create_ex(bfe2_beam** out, int64_t n_elem, const double* coords, c
     h->prec = precision;
     h->N = n_elem + 1;
     h->n = 3 * h->N;
-    // auto: partitions of ~64 nodes, at most 4096 of them (the separator system is eliminated sequentially)
-    int P = n_partitions > 0 ? n_partitions : (int)std::min<long long>(4096, std::max<long long>(1, h->N / 64));
+    // auto: ~sqrt(N) partitions -- the interiors (length N/P, thread per partition x rhs) and the separator system
+    // (length P, eliminated sequentially) are then equally long chains; measured at n = 1e5 in double-double: P = 256
+    // 2.4 ms per solve, 1024 3.5 ms, 1562 4.9 ms, 4096 12 ms (profiles/r2_config4_partitions.txt)
+    int P = n_partitions > 0 ? n_partitions : (int)std::min<long long>(4096, std::max<long long>(1, (long long)sqrt((double)h->N)));
     while (P > 1 && h->N < 3LL * P) --P;               // every partition needs at least one interior node
     h->P = P;
     std::vector<int> sep(P + 1);

@@ -53,7 +53,8 @@ __host__ __device__ inline SmemLayout make_layout(int nN, int nE, int n, int hbw
     L.invM = o;   o += n;
     o = (o + 1) & ~1;                                   // 16-byte align the big region
     L.U = o;
-    o += imax3(72 * nE, C * (n + 3 * nN + 6 * nE), (npad > 0 && npad * LD < 640) ? 640 : npad * LD);
+    // static phase: f, ufull, ef + room for the dense expansion of compact loads (f_nodal, r_local)
+    o += imax3(72 * nE, C * (n + 6 * nN + 12 * nE), (npad > 0 && npad * LD < 640) ? 640 : npad * LD);
     L.lam = o;    o += npad;
     L.order = o;  o += (npad + 1) / 2 + 1;              // npad int32 + 2 flags, stored in double slots
     L.total = o;
@@ -575,7 +576,9 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
                                              double* s_f, double* s_ufull, double* s_ef,
                                              const double* g_f_nodal, const double* g_r_local,
                                              double* g_u, double* g_ef, double* g_react, int tid, int nt,
-                                             bool clean = false) {
+                                             bool clean = false, const int32_t* fixed_pos = nullptr, int n_fixed = 0) {
+    // fixed_pos != nullptr: compact outputs -- u on the free DOFs only ([C, n]), reactions at the supported
+    // positions only ([C, n_fixed]; Results.py:129-143 reads them nowhere else)
     const int n = P.n, sumdof = P.sumdof, nE = P.nE;
     // 1. right-hand sides in free numbering
     for (int t = tid; t < C * n; t += nt) {
@@ -609,8 +612,10 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
         const int j = P.free_of_pos[pos];
         const double v = (j >= 0) ? s_f[c * n + j] : 0.0;
         s_ufull[t] = v;
-        g_u[t] = v;
+        if (fixed_pos == nullptr) g_u[t] = v;
     }
+    if (fixed_pos != nullptr)
+        for (int t = tid; t < C * n; t += nt) g_u[t] = s_f[t];
     scope_sync<WARP_SCOPE>();
     if (g_ef == nullptr && g_react == nullptr) return;
     // 4. local end forces per (load case, beam)
@@ -649,8 +654,9 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
     if (g_react == nullptr) return;
     scope_sync<WARP_SCOPE>();
     // 5. global reactions per (load case, position)
-    for (int t = tid; t < C * sumdof; t += nt) {
-        const int c = t / sumdof, pos = t % sumdof;
+    const int nr = fixed_pos ? n_fixed : sumdof;
+    for (int t = tid; t < C * nr; t += nt) {
+        const int c = t / nr, pos = fixed_pos ? fixed_pos[t % nr] : t % nr;
         const int node = pos / 3, k = pos % 3;
         double v = 0.0;
         for (int q = P.node_ptr[node]; q < P.node_ptr[node + 1]; ++q) {
@@ -662,7 +668,7 @@ __device__ __forceinline__ void stage_static(const PlanDev& P, int C, const doub
             else if (k == 1) v += sn * f[0] + cs * f[1];
             else v += f[2];
         }
-        g_react[t] = v - g_f_nodal[t];
+        g_react[t] = v - g_f_nodal[c * sumdof + pos];
     }
 }
 
@@ -1189,7 +1195,7 @@ template <int LPP>
 __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
                                                    double* s_W, double* s_lam, int* s_order, int n_modes,
                                                    double* g_lam, double* g_phi, int tid, int nt,
-                                                   bool clean = false) {
+                                                   bool clean = false, bool compact = false) {
     const int n = P.n, npad = P.npad, LD = P.LD;
     // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
     for (int s = tid; s < npad; s += nt) {
@@ -1225,6 +1231,10 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
         for (int r = 0; r < n; ++r) w[r] *= sign;
     }
     __syncthreads();
+    if (compact) {                                       // shapes on the free DOFs only: [n_modes, n]
+        for (int t = tid; t < n_modes * n; t += nt) g_phi[t] = s_W[s_order[t / n] * LD + t % n];
+        return;
+    }
     for (int t = tid; t < n_modes * P.sumdof; t += nt) {
         const int m = t / P.sumdof, pos = t % P.sumdof;
         const int j = P.free_of_pos[pos];

@@ -239,16 +239,15 @@ def run_gpu_arm(args):
     value = B * world / (ms_per_step * 1e-3)
     kernel_ms = ms_per_step                         # one fused launch per step
 
-    # ---- e2e: host buffers through the public HostPipeline API
-    pipe = batch.HostPipeline(plan, N_LC, N_MODES, chunk=args.chunk, n_streams=3, device=dev)
+    # ---- e2e: host buffers through the public HostPipeline API (packed records, compact load / result layouts)
+    io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=N_MODES)
+    pipe = batch.HostPipeline(plan, N_LC, N_MODES, chunk=args.chunk, n_streams=3, device=dev, io=io)
     h_in, h_out = pipe.alloc_host(B)
-    for k in h_in:
-        h_in[k].copy_(pk[k].cpu())
+    io.pack_inputs(h_in, *[pk[k].cpu() for k in ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')])
     for _ in range(2):
         pipe.run(h_in, h_out)
     bdist.barrier()
     torch.cuda.synchronize()
-    l0 = pipe.launches
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -261,7 +260,14 @@ def run_gpu_arm(args):
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
     bi, bo = pipe.bytes_per_structure()
     e2e_value = B * world / (e2e_ms * 1e-3)
-    e2e_ok = bool(torch.equal(h_out['lam'], out['lam'].cpu()) and torch.equal(h_out['u'], out['u'].cpu()))
+    hv = io.out_views(h_out)
+    pos = torch.as_tensor(plan.pos_of_free.astype('int64'))
+    fixed = torch.as_tensor(plan.fixed.astype('int64'))
+    e2e_ok = bool(torch.equal(hv['lam'], out['lam'].cpu()) and torch.equal(hv['u'], out['u'].cpu()[:, :, pos])
+                  and torch.equal(hv['phi'], out['phi'].cpu()[:, :, pos])
+                  and torch.equal(hv['endforces'], out['endforces'].cpu())
+                  and torch.equal(hv['reactions'], out['reactions'].cpu()[:, :, fixed])
+                  and torch.equal(hv['info'], out['info'].cpu()))
 
     # ---- final gather of summaries (off the timed path)
     table = bdist.gather_summaries(bdist.summarize(out['u'], out['lam'], out['info']), B * world)
@@ -296,6 +302,8 @@ def run_gpu_arm(args):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': bi * B, 'd2h_bytes_per_step': bo * B,
                 'ms_per_step': e2e_ms, 'wall_ms_per_step': e2e_wall * 1e3, 'chunk': args.chunk,
+                'copies_per_chunk': 2, 'layout': 'packed records: non-zero load entries in (%d of %d doubles), u / phi '
+                'on the free DOFs and reactions at the supports out' % (io.w_in, 713),
                 'matches_device_run': e2e_ok, 'numa_node': numa},
         'gpu_launches': args.steps,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',

@@ -137,6 +137,29 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
                      double* u, double* endforces, double* reactions,
                      double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream);
 
+/* ---- the same fused path on PACKED RECORDS with compact load / result layouts: the end-to-end entry for data
+ *      that lives in HOST memory (one copy per direction per chunk; only numbers that carry information travel).
+ *      A pattern is created once per (plan, load layout):
+ *        f_index [nnz_f]  dense indices lc*sumdof + pos of the entries of f_nodal that may be non-zero
+ *                         (Structure.add_nodal_load touches a handful of positions, Structure.py:258-287)
+ *        r_index [nnz_r]  dense indices (lc*nE + e)*6 + k into r_local (Structure.add_internal_loads, :244-248)
+ *      (HOST pointers; entries outside the pattern are zero for every structure of the batch).
+ *      Input record  [w_in]  = coords [nN,2] | props [nE,4] | nodal_mass [nN,2] | f values [nnz_f] | r values [nnz_r]
+ *      Output record [w_out] = u [C, n] on the FREE DOFs (the reference re-inserts the zero rows on the host,
+ *                              Solver.py:57-65) | endforces [C, nE, 6] | reactions [C, n_fixed] at the supported
+ *                              positions in positions_to_eliminate order (all Results.py:129-143 ever reads) |
+ *                              lam [n] | phi [n_modes, n] on the free DOFs | info, sweeps (two int32 in one slot)
+ *      bfe2_pattern_layout reports the widths and the offsets (in doubles) of the 5 input / 6 output fields.
+ *      in_rec [B, w_in], out_rec [B, w_out] are DEVICE pointers.  Results are bit-identical to bfe2_solve_fused. ---- */
+typedef struct bfe2_pattern bfe2_pattern;
+int  bfe2_pattern_create(bfe2_pattern** out, bfe2_plan* plan, int32_t C, int32_t do_modal, int32_t n_modes,
+                         int32_t nnz_f, const int32_t* f_index, int32_t nnz_r, const int32_t* r_index);
+void bfe2_pattern_destroy(bfe2_pattern* pattern);
+int  bfe2_pattern_layout(const bfe2_pattern* pattern, int32_t* in_width, int32_t* out_width,
+                         int32_t* in_offsets /*[5] or NULL*/, int32_t* out_offsets /*[6] or NULL*/);
+int  bfe2_solve_fused_packed(bfe2_plan* plan, bfe2_pattern* pattern, int64_t B, const double* in_rec,
+                             double* out_rec, void* stream);
+
 /* ---- small dense generalized symmetric eigenproblem A q = theta B q, A, B [Bt, n, n] row-major, B SPD
  *      (the Rayleigh-Ritz step of the subspace iteration below; same Cholesky-reduction + Jacobi kernel).
  *      V [Bt, n, n]: row k = k-th eigenvector, V B V^T = I.  workspace: 2*Bt*n*n doubles. ------------- */

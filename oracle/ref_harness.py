@@ -1,9 +1,10 @@
-"""Harness that drives the REAL reference (imported read-only from /root/reference)  --  TEST
-INFRASTRUCTURE for the build container only.
+"""Harness that drives the REAL reference  --  TEST / BASELINE INFRASTRUCTURE, never the product path.
 
-The reference cannot travel to the GPU box, so nothing under tests/ -m gpu, smoke() or bench.py
-imports this module; it is used by oracle/make_golden.py (fixture generation) and by the CPU-only
-pinning tests when /root/reference happens to be present.
+The reference is imported from the read-only checkout in the build container, or -- on the GPU box, where that
+checkout does not exist -- from baseline/_ref, the git-ignored `pip install --target` copy that
+install_into_baseline() makes (called by __graft_entry__.build()).  Users: oracle/make_golden.py (fixture
+generation), the CPU-only pinning tests, bench.py's reference arm (A) (object_path_seconds below) and
+tests/test_reference_suite.py (the reference's own Tests/ run through the GPU boundary).
 
 A "model" here is a plain dict:
     nodes      : list of (x, y)                      node k has ID k+1
@@ -20,12 +21,57 @@ import warnings
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('BEAMFE2_REFERENCE_ROOT', '/root/reference')
+REFERENCE_SOURCE = '/root/reference'                       # read-only checkout, build container only
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASELINE_REF = os.path.join(_REPO, 'baseline', '_ref')     # git-ignored install of the reference; travels to the GPU box
 _STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'mpl_stub')
 
 
+def _resolve_root():
+    env = os.environ.get('BEAMFE2_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir(os.path.join(REFERENCE_SOURCE, 'BeamFE2')):
+        return REFERENCE_SOURCE
+    return BASELINE_REF
+
+
+REFERENCE_ROOT = _resolve_root()
+
+
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'BeamFE2'))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'BeamFE2')) and os.path.isdir(os.path.join(REFERENCE_ROOT, 'drawing'))
+
+
+def install_into_baseline(verbose=False) -> bool:
+    """`pip install --target baseline/_ref` of the UNMODIFIED reference (the one offline install the task allows),
+    plus its `drawing` package (BeamFE2 imports it, setup.py does not list it) and its own `Tests/`, so that the
+    reference arm of bench.py and the reference's test-suite can run on the GPU box, where the read-only checkout
+    does not exist.  baseline/_ref is git-ignored: nothing of the reference enters the history.
+    Returns True when baseline/_ref is complete."""
+    import shutil
+    import subprocess
+    import tempfile
+    have = all(os.path.isdir(os.path.join(BASELINE_REF, d)) for d in ('BeamFE2', 'drawing', 'Tests'))
+    if have or not os.path.isdir(os.path.join(REFERENCE_SOURCE, 'BeamFE2')):
+        return have
+    os.makedirs(BASELINE_REF, exist_ok=True)
+    if not os.path.isdir(os.path.join(BASELINE_REF, 'BeamFE2')):
+        with tempfile.TemporaryDirectory() as tmp:         # setup.py writes egg-info next to itself: install from a copy
+            src = os.path.join(tmp, 'ref')
+            shutil.copytree(REFERENCE_SOURCE, src)
+            r = subprocess.run([sys.executable, '-m', 'pip', 'install', '--no-index', '--no-build-isolation', '--no-deps',
+                                '--find-links', '/opt/wheelhouse', '--target', BASELINE_REF, src],
+                               capture_output=True, text=True)
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout[-2000:] + r.stderr[-2000:])
+            if r.returncode != 0:
+                return False
+    for d in ('drawing', 'Tests'):
+        if not os.path.isdir(os.path.join(BASELINE_REF, d)):
+            shutil.copytree(os.path.join(REFERENCE_SOURCE, d), os.path.join(BASELINE_REF, d),
+                            ignore=shutil.ignore_patterns('__pycache__'))
+    return True
 
 
 def import_reference():
@@ -117,6 +163,26 @@ def run_reference(model, modal=True):
                 out['circular_freq'] = np.array(res.circular_frequencies)
                 out['shapes'] = np.stack([np.asarray(x).ravel() for x in res.displacement_results])
     return out
+
+
+def object_path_seconds(models):
+    """CPU baseline arm (A) of SURVEY.md 8(d): the reference's own object path, timed.  Per model: build
+    Node / HermitianBeam2D / Structure objects, every load case = clear + reload + solver['linear static'].solve()
+    + reaction_forces_asvector, then solver['modal'].solve() (Solver.py:29-87, Results.py:92-127).
+    Returns the seconds spent (imports excluded)."""
+    import time
+    import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t0 = time.perf_counter()
+        for model in models:
+            s = build_structure(model)
+            for lc in model.get('load_cases', []):
+                apply_load_case(s, lc)
+                assert s.solver['linear static'].solve()
+                s.results['linear static'].reaction_forces_asvector
+            assert s.solver['modal'].solve()
+        return time.perf_counter() - t0
 
 
 def pack_model(model):

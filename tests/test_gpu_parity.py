@@ -506,21 +506,89 @@ def test_one_plan_from_two_host_threads():
             assert torch.equal(lam, ref[0]) and torch.equal(u, ref[1])
 
 
-@pytest.mark.parametrize('modal', [True, False])
-def test_host_pipeline_equals_the_device_call(modal):
-    """The end-to-end path (pinned host buffers, chunks over three streams, ragged last chunk, staging buffers
-    reused) returns exactly what one device-resident call returns."""
-    P, pk, plan = p20_batch(1000)
-    pipe = batch.HostPipeline(plan, n_loadcases=3, n_modes=6, chunk=333, modal=modal)
-    h_in, h_out = pipe.alloc_host(1000)
-    for k in pipe.IN_KEYS:
-        h_in[k].copy_(pk[k].cpu())
-    pipe.run(h_in, h_out)
-    assert pipe.launches == 4
+def _compare_packed(io, views, ref, plan, modal, exact):
+    """compact results of the packed path against the dense tensors of solve_fused"""
+    pos = torch.as_tensor(plan.pos_of_free.astype('int64'), device=ref['info'].device)
+    fixed = torch.as_tensor(plan.fixed.astype('int64'), device=ref['info'].device)
+
+    def same(a, b, name):
+        if exact:
+            assert torch.equal(a, b), name
+        else:
+            assert ((a - b).abs().max() / b.abs().max()).item() < 1e-12, name
+    same(views['u'], ref['u'][:, :, pos], 'u')
+    same(views['endforces'], ref['endforces'], 'endforces')
+    same(views['reactions'], ref['reactions'][:, :, fixed], 'reactions')
+    assert torch.equal(views['info'], ref['info'])
+    if modal:
+        same(views['lam'], ref['lam'], 'lam')
+        same(views['phi'], ref['phi'][:, :, pos], 'phi')
+        assert torch.equal(views['sweeps'], ref['sweeps'])
+    dense = io.expand(views)
+    same(dense['u'], ref['u'], 'u dense')
+    assert (dense['u'][:, :, fixed] == 0).all()
+    if modal:
+        same(dense['phi'], ref['phi'], 'phi dense')
+
+
+@pytest.mark.parametrize('modal,compact_loads', [(True, True), (True, False), (False, True)])
+def test_packed_records_equal_the_dense_call(modal, compact_loads):
+    """bfe2_solve_fused_packed (one record per structure, non-zero load entries only, u / phi on the free DOFs,
+    reactions at the supports) returns bit for bit what bfe2_solve_fused returns on the dense tensors.  Static-only
+    runs go through the block-per-structure kernel instead of the 16-lane group kernel: same arithmetic up to the
+    order of the substitutions, compared to 1e-12."""
+    P, pk, plan = p20_batch(777)
+    if compact_loads:
+        io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=6, modal=modal)
+        assert io.f_index.tolist() == [21, 2 * 63 + 21, 2 * 63 + 41]            # FX node 8 (LC1, LC3), MZ node 14 (LC3)
+        assert io.r_index.size == 2 * 6 * 4                                     # 6 girder beams x (V, M) x 2 ends, LC2 + LC3
+        assert io.w_in == 42 + 80 + 42 + 3 + 48
+        assert io.w_out == 3 * 57 + 360 + 18 + (57 + 6 * 57 if modal else 0) + 1
+    else:
+        io = batch.PackedIO(plan, 3, 6, modal)
+        assert io.w_in == 42 + 80 + 42 + 189 + 360
+    rec = torch.zeros((777, io.w_in), dtype=torch.float64, device=DEV)
+    io.pack_inputs(rec, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'])
+    out = io.solve(rec)
     ref = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
                             modal=modal, n_modes=6)
-    keys = ('u', 'endforces', 'reactions', 'info') + (('lam', 'phi', 'sweeps') if modal else ())
-    for k in keys:
-        assert torch.equal(h_out[k], ref[k].cpu()), k
+    assert (ref['info'] == 0).all()
+    _compare_packed(io, io.out_views(out), ref, plan, modal, exact=modal)
+
+
+def test_packed_records_failure_codes_and_nan_fill():
+    P, pk, plan = p20_batch(8)
+    io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=4)
+    props = pk['props'].clone()
+    props[2, :, 0] = -props[2, :, 0]               # K not positive definite: everything NaN
+    props[5, :, 3] = 0.0                           # massless, no nodal mass below: modal NaN, static valid
+    rec = torch.zeros((8, io.w_in), dtype=torch.float64, device=DEV)
+    io.pack_inputs(rec, pk['coords'], props, None, pk['f_nodal'], pk['r_local'])
+    v = io.out_views(io.solve(rec))
+    info = v['info'].cpu().numpy()
+    assert info[2] == 1 and info[5] == -1 and (np.delete(info, [2, 5]) == 0).all()
+    assert torch.isnan(v['u'][2]).all() and torch.isnan(v['reactions'][2]).all() and torch.isnan(v['lam'][2]).all()
+    assert torch.isnan(v['lam'][5]).all() and torch.isnan(v['phi'][5]).all() and torch.isfinite(v['u'][5]).all()
+    ok = [b for b in range(8) if b not in (2, 5)]
+    assert torch.isfinite(v['u'][ok]).all() and torch.isfinite(v['phi'][ok]).all()
+
+
+@pytest.mark.parametrize('modal', [True, False])
+def test_host_pipeline_equals_the_device_call(modal):
+    """The end-to-end path (pinned host records, chunks over three streams, ragged last chunk, staging buffers
+    reused, ONE copy per direction per chunk) returns exactly what one device-resident call returns."""
+    P, pk, plan = p20_batch(1000)
+    io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=6, modal=modal)
+    pipe = batch.HostPipeline(plan, n_loadcases=3, n_modes=6, chunk=333, modal=modal, io=io)
+    h_in, h_out = pipe.alloc_host(1000)
+    io.pack_inputs(h_in, pk['coords'].cpu(), pk['props'].cpu(), pk['nodal_mass'].cpu(), pk['f_nodal'].cpu(),
+                   pk['r_local'].cpu())
+    pipe.run(h_in, h_out)
+    assert pipe.launches == 4 and pipe.copies == 8
+    ref = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
+                            modal=modal, n_modes=6)
+    ref = {k: (v.cpu() if v is not None else None) for k, v in ref.items()}
+    _compare_packed(io, io.out_views(h_out), ref, plan, modal, exact=modal)
     bi, bo = pipe.bytes_per_structure()
-    assert bi == 8 * (42 + 80 + 42 + 189 + 360)
+    assert bi == 8 * (42 + 80 + 42 + 3 + 48)
+    assert bo == 8 * (171 + 360 + 18 + (57 + 342 if modal else 0) + 1)

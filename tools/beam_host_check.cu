@@ -5,6 +5,7 @@
 // Build:  nvcc -O2 -std=c++17 -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -o /tmp/libbeam_host.so tools/beam_host_check.cu
 // Driver: tools/beam_host_check.py
 #include <cstdint>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -26,7 +27,7 @@ template <class S> static HostBeam<S>* create(long long n_elem, const double* co
     auto* h = new HostBeam<S>();
     h->N = n_elem + 1;
     const long long N = h->N;
-    if (P <= 0) P = (int)std::min<long long>(4096, std::max<long long>(1, N / 64));
+    if (P <= 0) P = (int)std::min<long long>(4096, std::max<long long>(1, (long long)sqrt((double)N)));
     while (P > 1 && N < 3LL * P) --P;
     h->P = P;
     h->sep.resize(P + 1);
