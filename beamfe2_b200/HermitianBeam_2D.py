@@ -11,6 +11,8 @@ import math
 import numpy as np
 
 from . import Loads as BL
+# the reference does `from BeamFE2.helpers import *` (HermitianBeam_2D.py:4): user code reaches these through HB.*
+from .helpers import compile_global_matrix, np_matrix_tolist, transfer_matrix  # noqa: F401
 
 
 class HermitianBeam2D(object):
@@ -66,7 +68,8 @@ class HermitianBeam2D(object):
         def t(v):
             return torch.tensor([float(v)], dtype=torch.float64, device='cuda')
         lump = torch.tensor([1 if self.mass_matrix == 'lumped' else 0], dtype=torch.uint8, device='cuda')
-        Kg, Mg = batch.element_km(*(t(v) for v in xy), t(self.E), t(self.A), t(self.I), t(self.rho), lump)
+        Kg, Mg = batch.element_km(*(t(v) for v in xy), t(self.E), t(self.A), t(self.I),
+                                    t(0.0 if self.rho is None else self.rho), lump)   # rho is optional for static-only models
         return Kg[0].cpu().numpy(), Mg[0].cpu().numpy()
 
     @property

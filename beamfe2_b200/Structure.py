@@ -157,19 +157,29 @@ class Structure(object):
             if q.hbw < p.hbw:
                 p = q
         coords = np.array([[float(n.x), float(n.y)] for n in nodes])
-        props = np.array([[float(b.E), float(b.A), float(b.I), float(b.rho)] for b in self.beams])
+        props = np.array([[float(b.E), float(b.A), float(b.I), float(b.rho if b.rho is not None else 0.0)] for b in self.beams])
         mass = np.zeros((nN, 2))
         if self._mass_vector is not None:
             mv = np.asarray(self._mass_vector).ravel()
             mass[:, 0], mass[:, 1] = mv[0::3], mv[1::3]
-        f_nodal = np.zeros((1, 3 * nN))
-        for ld in self.nodal_loads:
-            k = (ld.node.ID - 1) * 3
-            f_nodal[0, k:k + 3] += np.asarray(ld.asvector).ravel()
         r_local = np.zeros((1, nE, 6))
         for e, b in enumerate(self.beams):
             for ld in b.internal_loads:
                 r_local[0, e] += np.asarray(ld.reactions_asvector).ravel()
+        # The reference solves with _load_vector (Solver.py:83), whatever call filled it (add_nodal_load,
+        # add_internal_loads or add_single_dynam_to_node directly).  The kernel takes the nodal part and the beam
+        # part separately (it needs r_local again for the end forces) and adds T(alpha) r_local itself, so the nodal
+        # part is _load_vector minus that: the right-hand side is the reference's in every case.
+        f_nodal = np.zeros((1, 3 * nN))
+        if self._load_vector is not None:
+            f_nodal[0] = np.asarray(self._load_vector, dtype=np.float64).ravel()
+            for e, b in enumerate(self.beams):
+                if not np.any(r_local[0, e]):
+                    continue
+                c, s = np.cos(b.direction), np.sin(b.direction)
+                R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+                f_nodal[0, 3 * conn[e, 0]:3 * conn[e, 0] + 3] -= R @ r_local[0, e, :3]
+                f_nodal[0, 3 * conn[e, 1]:3 * conn[e, 1] + 3] -= R @ r_local[0, e, 3:]
         return p, dict(coords=coords, props=props, nodal_mass=mass, f_nodal=f_nodal, r_local=r_local)
 
     # ---- matrices (CUDA assembly kernel K2 on the uncondensed plan)

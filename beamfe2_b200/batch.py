@@ -140,20 +140,30 @@ def solve_fused(plan: Plan, coords, props, nodal_mass=None, f_nodal=None, r_loca
     return dict(u=u, endforces=ef, reactions=re, lam=lam, phi=phi, info=info, sweeps=sweeps)
 
 
-def internal_actions(plan: Plan, coords, endforces, q_axial=None, q_perp=None, npts=11, want_field=True):
-    """N, V, M along every beam: actions [B,C,nE,3,npts] (or None) and maxabs [B,C,nE,3]."""
+LOAD_KINDS = {'concentrated perpendicular force': 1, 'concentrated axial force': 2, 'concentrated moment': 3}
+
+
+def internal_actions(plan: Plan, coords, endforces, q_axial=None, q_perp=None, npts=11, want_field=True, conc=None):
+    """N / V / M at npts equidistant positions of every beam (HermitianBeam_2D.py:398-431) and their per-beam maxima.
+    q_axial / q_perp [B, C, nE]: uniform beam loads; conc [B, C, nE, n_conc, 3]: up to n_conc concentrated loads per
+    beam as (kind, value, normalised position), kind from LOAD_KINDS (0 = empty slot).
+    Returns (actions [B, C, nE, 3, npts] or None, maxabs [B, C, nE, 3])."""
     B, C = endforces.shape[0], endforces.shape[1]
     dev = endforces.device
     coords = _chk(coords, (B, plan.n_nodes, 2), 'coords')
     endforces = _chk(endforces, (B, C, plan.n_elem, 6), 'endforces')
     q_axial = _chk(q_axial, (B, C, plan.n_elem), 'q_axial')
     q_perp = _chk(q_perp, (B, C, plan.n_elem), 'q_perp')
+    n_conc = 0
+    if conc is not None:
+        n_conc = int(conc.shape[3])
+        conc = _chk(conc, (B, C, plan.n_elem, n_conc, 3), 'conc')
     act = torch.empty((B, C, plan.n_elem, 3, npts), dtype=torch.float64, device=dev) if want_field else None
     mx = torch.empty((B, C, plan.n_elem, 3), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().bfe2_internal_actions(plan.handle, B, C, int(npts), _lib.ptr(coords), _lib.ptr(endforces),
-                                                    _lib.ptr(q_axial), _lib.ptr(q_perp), _lib.ptr(act), _lib.ptr(mx),
-                                                    _stream_ptr()))
+        _lib.check(_lib.lib().bfe2_internal_actions_ex(plan.handle, B, C, int(npts), _lib.ptr(coords), _lib.ptr(endforces),
+                                                       _lib.ptr(q_axial), _lib.ptr(q_perp), n_conc, _lib.ptr(conc),
+                                                       _lib.ptr(act), _lib.ptr(mx), _stream_ptr()))
     return act, mx
 
 

@@ -2,8 +2,9 @@
 //
 //   bfe2_internal_actions : N / V / M along every beam from the local end forces (HermitianBeam_2D.py:398-431:
 //       axial, shear: -v1; moment: v1 + (-v2 - v1) pos) plus the add-on curves of UNIFORM beam loads
-//       (Loads.py:214-225 axial: -xi q L;  :277-289 shear: -xi L q, moment: xi (1-xi) q L^2 / 2), and the
-//       per-beam maxima the reference lists as future work (todo.md:23).
+//       (Loads.py:214-225 axial: -xi q L;  :277-289 shear: -xi L q, moment: xi (1-xi) q L^2 / 2) and of the three
+//       CONCENTRATED ones (Loads.py:347-365, 421-432, 489-502), and the per-beam maxima the reference lists as
+//       future work (todo.md:23) -- with the one-sided limits at the load positions, where the curves jump.
 //   bfe2_modal_participation : Gamma_k = phi_k^T M r for the rigid-body influence vectors r_x, r_y
 //       (prototype arithmetic in Examples/modal_masses.py:40-49; phi is M-normalised, so the effective modal
 //       mass is Gamma^2).
@@ -19,10 +20,37 @@ int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out);   // bfe2.cu: view on 
 
 namespace {
 
+// add-on curves of the concentrated beam loads at normalised position xi (Loads.py:347-365 perpendicular force,
+// :421-432 axial force, :489-502 moment), with the reference's own comparisons at xi == position.  `side` != 0
+// evaluates the one-sided limit at the position of load `kink` instead (left: -1, right: +1) -- used for the maxima,
+// because shear / axial / moment jump there.
+__device__ __forceinline__ void conc_addon(const double* __restrict__ cl, int n_conc, double xi, double L, int kink,
+                                           int side, double& ax, double& sh, double& mo) {
+    for (int j = 0; j < n_conc; ++j) {
+        const int kind = (int)cl[3 * j];
+        if (kind == 0) continue;
+        const double P = cl[3 * j + 1], a = cl[3 * j + 2];
+        bool below = xi < a, above = xi > a;             // the reference's tests
+        if (j == kink && side != 0) { below = side < 0; above = side > 0; }
+        if (kind == BFE2_LOAD_CONC_PERP) {
+            double m = (1.0 - a) * P * xi;
+            if (above) m -= fabs(xi - a) * P;
+            mo += m * L;
+            sh += below ? 0.0 : -P;
+        } else if (kind == BFE2_LOAD_CONC_AXIAL) {
+            ax += below ? 0.0 : -P;
+        } else if (kind == BFE2_LOAD_CONC_MOMENT) {
+            double m = -(P / L) * xi * L;
+            if (above) m += P;
+            mo += m;
+        }
+    }
+}
+
 __global__ void k_internal_actions(PlanDev P, long long B, int C, int npts, const double* __restrict__ coords,
                                    const double* __restrict__ endforces, const double* __restrict__ q_axial,
-                                   const double* __restrict__ q_perp, double* __restrict__ actions,
-                                   double* __restrict__ maxabs) {
+                                   const double* __restrict__ q_perp, int n_conc, const double* __restrict__ conc,
+                                   double* __restrict__ actions, double* __restrict__ maxabs) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = B * C * P.nE;
     if (t >= total) return;
@@ -34,20 +62,40 @@ __global__ void k_internal_actions(PlanDev P, long long B, int C, int npts, cons
     beam_geometry(xy[2 * ni], xy[2 * ni + 1], xy[2 * nj], xy[2 * nj + 1], L, c, s);
     const double* q = endforces + t * 6;
     const double qa = q_axial ? q_axial[t] : 0.0, qp = q_perp ? q_perp[t] : 0.0;
+    const double* cl = (conc && n_conc > 0) ? conc + t * 3 * n_conc : nullptr;
+    const int nc = cl ? n_conc : 0;
     const double n1 = q[0], v1 = q[1], m1 = q[2], m2 = -q[5];
     double mx[3] = {0.0, 0.0, 0.0};
+    auto eval = [&](double xi, int kink, int side, double& ax, double& sh, double& mo) {
+        ax = -n1 + (-xi * qa * L);
+        sh = -v1 + (xi * L * -qp);
+        mo = (m1 + (m2 - m1) * xi) + ((xi * (1.0 - xi)) * qp * (L * L)) / 2.0;
+        if (nc) conc_addon(cl, nc, xi, L, kink, side, ax, sh, mo);
+    };
     for (int k = 0; k < npts; ++k) {
         const double xi = npts > 1 ? (double)k / (double)(npts - 1) : 0.0;
-        const double ax = -n1 + (-xi * qa * L);
-        const double sh = -v1 + (xi * L * -qp);
-        const double mo = (m1 + (m2 - m1) * xi) + ((xi * (1.0 - xi)) * qp * (L * L)) / 2.0;
+        double ax, sh, mo;
+        eval(xi, -1, 0, ax, sh, mo);
         if (actions) {
             double* o = actions + t * 3 * npts;
             o[k] = ax; o[npts + k] = sh; o[2 * npts + k] = mo;
         }
         mx[0] = fmax(mx[0], fabs(ax)); mx[1] = fmax(mx[1], fabs(sh)); mx[2] = fmax(mx[2], fabs(mo));
     }
-    if (maxabs) { maxabs[t * 3] = mx[0]; maxabs[t * 3 + 1] = mx[1]; maxabs[t * 3 + 2] = mx[2]; }
+    if (maxabs) {
+        // the extrema of piecewise-linear shear / axial curves and the moment kinks sit at the load positions: both
+        // one-sided limits there join the sampled values
+        for (int j = 0; j < nc; ++j) {
+            if ((int)cl[3 * j] == 0) continue;
+            const double a = cl[3 * j + 2];
+            for (int side = -1; side <= 1; side += 2) {
+                double ax, sh, mo;
+                eval(a, j, side, ax, sh, mo);
+                mx[0] = fmax(mx[0], fabs(ax)); mx[1] = fmax(mx[1], fabs(sh)); mx[2] = fmax(mx[2], fabs(mo));
+            }
+        }
+        maxabs[t * 3] = mx[0]; maxabs[t * 3 + 1] = mx[1]; maxabs[t * 3 + 2] = mx[2];
+    }
 }
 
 // thread per (structure, mode): Gamma = sum_i phi_i (M r)_i with the lower-band M of the condensed system
@@ -82,20 +130,28 @@ __global__ void k_participation(PlanDev P, long long B, int n_modes, const doubl
 
 extern "C" {
 
-int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
-                          const double* endforces, const double* q_axial, const double* q_perp, double* actions,
-                          double* maxabs, void* stream) {
+int bfe2_internal_actions_ex(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
+                             const double* endforces, const double* q_axial, const double* q_perp, int32_t n_conc,
+                             const double* conc, double* actions, double* maxabs, void* stream) {
     if (plan && B == 0) return 0;
-    if (!plan || B < 0 || C < 1 || npts < 1 || !coords || !endforces || (!actions && !maxabs))
+    if (!plan || B < 0 || C < 1 || npts < 1 || !coords || !endforces || (!actions && !maxabs) || n_conc < 0 ||
+        (n_conc > 0 && !conc))
         return bfe2_fail(-1, "bfe2_internal_actions: bad argument");
     PlanDev pd;
     if (const int r = bfe2_plan_device_view(plan, &pd)) return r;
     const PlanDev* P = &pd;
     const long long total = B * C * P->nE;
-    k_internal_actions<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, B, C, npts, coords, endforces,
-                                                                                           q_axial, q_perp, actions, maxabs);
+    k_internal_actions<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        *P, B, C, npts, coords, endforces, q_axial, q_perp, n_conc, conc, actions, maxabs);
     if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_internal_actions launch failed");
     return 0;
+}
+
+int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
+                          const double* endforces, const double* q_axial, const double* q_perp, double* actions,
+                          double* maxabs, void* stream) {
+    return bfe2_internal_actions_ex(plan, B, C, npts, coords, endforces, q_axial, q_perp, 0, nullptr, actions, maxabs,
+                                    stream);
 }
 
 int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,

@@ -26,7 +26,7 @@ def compile_global_matrix(beams, stiffness=False, mass=False, geometrical=False)
     def dev(a):
         return torch.as_tensor(np.ascontiguousarray(a)[None], dtype=torch.float64, device='cuda')
     coords = dev([[float(n.x), float(n.y)] for n in nodes])
-    props = dev([[float(b.E), float(b.A), float(b.I), float(b.rho)] for b in beams])
+    props = dev([[float(b.E), float(b.A), float(b.I), float(b.rho if b.rho is not None else 0.0)] for b in beams])
     Kb, Mb = batch.assemble_banded(plan, coords, props, None, want_mass=bool(mass))
     torch.cuda.synchronize()
     band = (Kb if stiffness else Mb)[0].cpu().numpy()

@@ -72,6 +72,62 @@ def cpu_oracle_throughput(per_worker: int, workers: int):
     return per_worker * workers / wall, wall
 
 
+def _ref_worker(args):
+    """One host process: the REAL reference (baseline/_ref) on `count` P20 variants through its own object path
+    (SURVEY.md 8d arm (A)); returns seconds, or a string when the reference is not installed."""
+    shard, count = args
+    os.environ['OMP_NUM_THREADS'] = '1'
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    from beamfe2_b200 import sweep
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return 'reference not installed under baseline/_ref (run __graft_entry__.build() where the checkout exists)'
+    P = sweep.p20_draw_params(count, shard=2000 + shard)
+    models = [sweep.p20_model_dict(P[k]) for k in range(count)]
+    rh.object_path_seconds(models[:1])                                   # imports, first-call costs
+    return rh.object_path_seconds(models)
+
+
+def cpu_reference_throughput(per_worker: int, workers: int):
+    """structures/s of the unmodified reference with `workers` single-threaded processes; None if unavailable."""
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        secs = pool.map(_ref_worker, [(w, per_worker) for w in range(workers)])
+        wall = time.perf_counter() - t0
+    if any(isinstance(x, str) for x in secs):
+        return None, [x for x in secs if isinstance(x, str)][0]
+    # the workers run side by side: throughput = total structures / the slowest worker's solve time
+    return per_worker * workers / max(secs), wall
+
+
+def cpu_arms(port_per_worker: int, ref_total: int = 256):
+    """All four CPU arms of SURVEY.md 8(d): the real reference (A) and the numpy/scipy oracle port (B), each on one
+    core and on every host core."""
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    arms = []
+    for w in (1, workers):
+        per = max(8, ref_total // w) if w > 1 else min(ref_total, 200)
+        v, info = cpu_reference_throughput(per, w)
+        a = {'kind': 'reference', 'cores': w, 'unit': UNIT,
+             'sample': '%d P20 variants through the unmodified BeamFE2 objects from baseline/_ref: Node / HermitianBeam2D / '
+                       'Structure, 3 x (clear + load + linear static solve + reaction_forces_asvector) + modal solve' % (per * w)}
+        if v is None:
+            a['unavailable'] = info
+        else:
+            a['value'] = v
+        arms.append(a)
+    for w in (1, workers):
+        per = port_per_worker if w > 1 else min(port_per_worker, 4096)
+        v, wall = cpu_oracle_throughput(per, w)
+        arms.append({'kind': 'port', 'cores': w, 'unit': UNIT, 'value': v,
+                     'sample': '%d P20 variants (%d per worker x %d single-threaded workers, %.1f s wall), numpy/scipy oracle '
+                               'port: dense assembly + numpy.linalg.solve + scipy.linalg.eigh(K, M)' % (per * w, per, w, wall)})
+    return arms, workers
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -91,12 +147,27 @@ def run_reference_arm(args):
     sample = '%d P20 variants per step (%d per worker x %d single-threaded workers), numpy/scipy oracle port of ' \
              'the reference path: dense assembly, numpy.linalg.solve, scipy.linalg.eigh(K, M)' % (
                  per_worker * workers, per_worker, workers)
+    # the unmodified reference through its own objects (arm (A)), one core and all cores, beside the port
+    arms = []
+    for w in (1, workers):
+        per = max(8, args.ref_sample // w) if w > 1 else min(args.ref_sample, 200)
+        rv, info = cpu_reference_throughput(per, w)
+        a = {'kind': 'reference', 'cores': w, 'unit': UNIT,
+             'sample': '%d P20 variants through the unmodified BeamFE2 objects (baseline/_ref): Node / HermitianBeam2D / '
+                       'Structure, 3 x (clear + load + linear static solve + reaction_forces_asvector) + modal solve' % (per * w)}
+        a.update({'unavailable': info} if rv is None else {'value': rv})
+        arms.append(a)
+    v1, _ = cpu_oracle_throughput(min(per_worker, 4096), 1)
+    arms.append({'kind': 'port', 'cores': 1, 'unit': UNIT, 'value': v1, 'sample': 'the port on one core'})
+    arms.append({'kind': 'port', 'cores': workers, 'unit': UNIT, 'value': value, 'sample': sample})
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, per_gpu=per_worker * workers),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
+        # headline = the FASTER of the two CPU arms (the vectorised numpy/scipy port, ~50x the reference's own
+        # object path), so the driver's GPU/CPU ratio is the conservative one; every arm is listed in `arms`
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample, 'arms': arms},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -317,15 +388,13 @@ def run_gpu_arm(args):
         'failed_structures': n_bad,
         'mean_sweeps': float(out['sweeps'].double().mean().item()),
     }
-    if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        workers = max(1, min(cores, 64))
-        v, wall = cpu_oracle_throughput(args.cpu_sample, workers)
-        line['cpu_baseline'] = {
-            'value': v, 'unit': UNIT, 'cores': workers, 'kind': 'port',
-            'sample': '%d P20 variants (%d per worker x %d single-threaded workers, %.1f s wall), numpy/scipy '
-                      'oracle port: dense assembly + numpy.linalg.solve + scipy.linalg.eigh(K, M)' % (
-                          args.cpu_sample * workers, args.cpu_sample, workers, wall)}
+    if not args.no_cpu:
+        # rank 0 only, after the timed regions and after the process group is gone; at N > 1 a smaller sample
+        arms, workers = cpu_arms(args.cpu_sample if world == 1 else max(1024, args.cpu_sample // 8),
+                                 args.ref_sample if world == 1 else max(64, args.ref_sample // 4))
+        port = [a for a in arms if a['kind'] == 'port' and a['cores'] == workers][-1]
+        line['cpu_baseline'] = {'value': port['value'], 'unit': UNIT, 'cores': workers, 'kind': 'port',
+                                'sample': port['sample'], 'arms': arms}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -339,6 +408,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=3125, help='HostPipeline chunk (structures)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=16384, help='CPU oracle: variants per worker')
+    ap.add_argument('--ref-sample', type=int, default=256, help='real reference (arm A): variants in total')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -219,6 +219,18 @@ int  bfe2_update64(int64_t n, const double* Z, const double* Q, double* Xout, vo
 int bfe2_internal_actions(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
                           const double* endforces, const double* q_axial, const double* q_perp,
                           double* actions, double* maxabs, void* stream);
+/*   ... plus the add-on curves of up to n_conc CONCENTRATED loads per beam (Loads.py:347-365 perpendicular force,
+ *     :421-432 axial force, :489-502 moment): conc [B, C, nE, n_conc, 3] = (kind, value, normalised position), kind
+ *     one of BFE2_LOAD_* (0 = empty slot).  Sampled values use the reference's own comparisons at xi == position;
+ *     maxabs also takes both one-sided limits at every load position (the curves jump / kink there). */
+#define BFE2_LOAD_NONE        0
+#define BFE2_LOAD_CONC_PERP   1
+#define BFE2_LOAD_CONC_AXIAL  2
+#define BFE2_LOAD_CONC_MOMENT 3
+int bfe2_internal_actions_ex(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
+                             const double* endforces, const double* q_axial, const double* q_perp,
+                             int32_t n_conc, const double* conc /*or NULL*/,
+                             double* actions, double* maxabs, void* stream);
 int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,
                              double* gamma, void* stream);
 

@@ -4,8 +4,8 @@ Run in the build container only:   python -m oracle.make_golden
 Outputs (committed):
     tests/golden/ref_cases.json   the model dicts (inputs) of every case
     tests/golden/ref_cases.npz    what the reference computed for them ("<case>/<quantity>")
-    tests/golden/p20_truth.npz    40-digit (mpmath) solutions of the assembled P20 matrices of the
-                                  first variants of the config-3 generator: a truth that is
+    tests/golden/p20_truth.npz    40-digit (mpmath) solutions of the assembled P20 matrices of 64 variants of
+                                  the config-3 generator (made by oracle/make_truth.py): a truth that is
                                   independent of any FP64 LAPACK route (scipy's own eigenvalues are
                                   only good to ~1e-10 relative on these pencils)
 
@@ -137,49 +137,11 @@ def p20_cases(n=4):
     return {('p20_v%d' % k): sweep.p20_model_dict(P[k]) for k in range(n)}
 
 
-def mp_truth(n_variants=8, n_modes=10):
-    """40-digit eigen/static solutions of the oracle-assembled P20 pencils."""
-    import mpmath as mp
-    import torch
-    from beamfe2_b200 import sweep
-    mp.mp.dps = 40
-    P = sweep.p20_draw_params(n_variants)
-    pk = {k: v.numpy() for k, v in sweep.p20_pack(torch.from_numpy(P)).items()}
-    conn, sup = sweep.p20_topology()
-    fixed = orc.positions_to_eliminate(sup)
-    o = orc.solve_batch(conn, fixed, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'])
-    keep = orc.free_positions(21, fixed)
-    lam_t = np.zeros((n_variants, 57))
-    phi_t = np.zeros((n_variants, n_modes, 63))
-    u_t = np.zeros((n_variants, 3, 63))
-    for b in range(n_variants):
-        K = mp.matrix(o['Kc'][b].tolist())
-        M = mp.matrix(o['Mc'][b].tolist())
-        Lm = mp.cholesky(M)
-        Li = mp.inverse(Lm)
-        Cm = Li * K * Li.T
-        Cm = (Cm + Cm.T) / 2
-        E, Q = mp.eigsy(Cm)
-        order = sorted(range(57), key=lambda k: E[k])
-        Phi = Li.T * Q
-        for r, k in enumerate(order):
-            lam_t[b, r] = float(E[k])
-            if r < n_modes:
-                col = [Phi[i, k] for i in range(57)]
-                nrm = mp.sqrt(sum(col[i] * sum(M[i, j] * col[j] for j in range(57)) for i in range(57)))
-                col = [c / nrm for c in col]
-                big = max(range(57), key=lambda i: abs(col[i]))
-                sgn = -1 if col[big] < 0 else 1
-                phi_t[b, r, keep] = [float(sgn * c) for c in col]
-        fc = o['f'][b][:, keep]
-        for c in range(3):
-            x = mp.lu_solve(K, mp.matrix(fc[c].tolist()))
-            u_t[b, c, keep] = [float(v) for v in x]
-        print('truth variant', b, 'done', flush=True)
-    return dict(params=P, lam=lam_t, phi=phi_t, u=u_t)
-
-
 POST_CASES = ('p20_v0', 'p20_v1', 'allresults_1', 'allresults_2', 'chopra_105')
+# cases with CONCENTRATED beam loads (Loads.py:347-365, 421-432, 489-502): 11 positions, so that xi = 0.3 -- the load
+# position of clamped_clamped_loads / cantilever_example -- is sampled exactly and the reference's own comparisons at
+# xi == position are pinned; n_free = 0 for clamped_clamped_loads (no modal part)
+POST_CASES_CONC = ('clamped_clamped_loads', 'vertical_beam', 'cantilever_example')
 
 
 def post_golden(models):
@@ -187,8 +149,8 @@ def post_golden(models):
     participation factors of Examples/modal_masses.py:40-49, computed by the REAL reference."""
     import warnings
     out = {}
-    pos = [0.0, 0.25, 0.5, 0.75, 1.0]
-    for name in POST_CASES:
+    for name in POST_CASES + POST_CASES_CONC:
+        pos = [0.0, 0.25, 0.5, 0.75, 1.0] if name in POST_CASES else [k / 10 for k in range(11)]
         model = models[name]
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -205,6 +167,8 @@ def post_golden(models):
                                      for a in ('axial', 'shear', 'moment')])
                 acts.append(per_beam)
             out[name + '/internal_actions'] = np.array(acts)
+            if name in POST_CASES_CONC:
+                continue
             s.solver['modal'].solve()
             m = np.asarray(s.M_with_masses)
             gam = []
@@ -225,6 +189,10 @@ def main():
     os.makedirs(gold, exist_ok=True)
     models = cases()
     models.update(p20_cases())
+    if '--post-only' in sys.argv:
+        np.savez_compressed(os.path.join(gold, 'ref_post.npz'), **post_golden(models))
+        print('wrote ref_post.npz')
+        return
     arrays = {}
     for name, model in models.items():
         n_free = 3 * len(model['nodes']) - len(orc.positions_to_eliminate(model['supports']))
@@ -241,8 +209,7 @@ def main():
         json.dump(models, f, default=enc, indent=0)
     np.savez_compressed(os.path.join(gold, 'ref_cases.npz'), **arrays)
     np.savez_compressed(os.path.join(gold, 'ref_post.npz'), **post_golden(models))
-    if '--no-truth' not in sys.argv:
-        np.savez_compressed(os.path.join(gold, 'p20_truth.npz'), **mp_truth())
+    # tests/golden/p20_truth.npz (40-digit solutions) is made by oracle/make_truth.py
     print('wrote', gold)
 
 

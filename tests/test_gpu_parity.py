@@ -165,10 +165,7 @@ def test_static_unfused_equals_fused_and_oracle():
         assert util.relmax(u[b], o['u'][b]) < 1e-10
         assert util.relmax(s['endforces'][b].cpu().numpy(), o['endforces'][b]) < 1e-10
         assert util.relmax(s['reactions'][b].cpu().numpy(), o['reactions'][b]) < 1e-10
-    t = util.p20_truth()                               # 40-digit solve of the same K, f
-    nt = t['u'].shape[0]
-    P, pk, plan = p20_batch(nt)                        # (the generator draws per-column [B] arrays)
-    assert np.array_equal(P, t['params'])
+    t, pk = util.p20_truth_batch(DEV)                  # 40-digit solve of the same K, f: 64 variants picked by condition
     s = batch.solve_fused(plan, pk['coords'], pk['props'], None, pk['f_nodal'], pk['r_local'], modal=False)
     assert util.relmax(s['u'].cpu().numpy(), t['u']) < 1e-10
 
@@ -207,45 +204,62 @@ def test_modal_golden(case):
 
 
 def test_modal_p20_truth_1e10():
-    """The north_star bar, against a 40-digit solution of the same pencils: eigenvalues and the first
-    10 M-normalised modes to 1e-10 relative."""
-    t = util.p20_truth()
-    nt = t['lam'].shape[0]
-    P, pk, plan = p20_batch(nt)
-    assert np.array_equal(P, t['params'])
+    """The north_star bar, against a 40-digit solution of the same pencils: ALL 57 eigenvalues and the first
+    10 M-normalised modes to 1e-10 relative, on 64 variants picked to span the sweep (lam_max / lam_min from 4.7e5 to
+    6.4e7, near-degenerate pairs down to a relative gap of 4e-5; oracle/make_truth.py).  Modes of a pair closer than
+    1e-3 are compared as a subspace."""
+    t, pk = util.p20_truth_batch(DEV)
+    conn, sup = sweep.p20_topology()
+    plan = Plan.from_supports(21, conn, sup)
     out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], pk['f_nodal'], pk['r_local'],
                             n_modes=10)
     assert (out['info'] == 0).all()
     lam = out['lam'].cpu().numpy()
     phi = out['phi'].cpu().numpy()
+    assert lam.shape[0] >= 64
     assert np.abs(lam / t['lam'] - 1).max() < 1e-10
-    assert util.mode_err(phi, t['phi']).max() < 1e-10
+    n_pairs = 0
+    for b in range(lam.shape[0]):
+        e = util.mode_err_clustered(phi[b], t['phi'][b], t['lam'][b])
+        n_pairs += int(np.sum(np.diff(t['lam'][b][:10]) / t['lam'][b][1:10] < 1e-3))
+        assert np.nanmax(e) < 1e-10, (b, str(t['kind'][b]), e)
+    assert n_pairs >= 16                                 # the close pairs really are in the fixture
     # sign convention: the largest-magnitude entry of every mode is positive
     big = np.take_along_axis(phi, np.abs(phi).argmax(axis=-1)[..., None], axis=-1)
     assert (big > 0).all()
 
 
-def test_modal_p20_vs_scipy_batch():
+@pytest.mark.parametrize('shard', [3, 5])
+def test_modal_p20_vs_scipy_batch(shard):
+    """400 variants per shard: every one of the 57 eigenvalues within 1e-10 of scipy's eigenpairs refined by one
+    extended-precision Rayleigh-quotient step (tests/util.py::refined_eigenvalues agrees with the 40-digit truth to
+    1e-13, tests/test_oracle_pinning.py).  The DIRECT comparison with scipy's own eigenvalues is kept beside it with
+    LAPACK's bound, because dsygvd itself is only absolutely accurate (up to 5e-10 off on the smallest ones)."""
     B = 400
-    P, pk, plan = p20_batch(B, shard=3)
+    P, pk, plan = p20_batch(B, shard=shard)
     out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'], None, None, n_modes=10)
     assert (out['info'] == 0).all()
     sw = out['sweeps'].cpu().numpy()
     assert sw.min() >= 5 and sw.max() <= 16
-    o = oracle_p20(pk, n_modes=10)
+    o = oracle_p20(pk, n_modes=57)
     lam = out['lam'].cpu().numpy()
-    bound = 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']            # scipy's own (LAPACK) error bound
-    assert (np.abs(lam / o['lam'] - 1) < bound).all()
-    # Rayleigh quotients of scipy's vectors in extended precision are second-order accurate: a much
-    # tighter reference for the eigenvalues than scipy's eigenvalues themselves
-    Kc, Mc = o['Kc'].astype(np.longdouble), o['Mc'].astype(np.longdouble)
     keep = plan.pos_of_free
-    V = o['phi'][:, :, keep].astype(np.longdouble)
-    rq = np.einsum('bmi,bij,bmj->bm', V, Kc, V) / np.einsum('bmi,bij,bmj->bm', V, Mc, V)
-    assert np.abs(lam[:, :10] / rq.astype(np.float64) - 1).max() < 1e-10
+    rq = util.refined_eigenvalues(o['Kc'], o['Mc'], o['phi'][:, :, keep])
+    assert np.abs(lam / rq - 1).max() < 1e-10                                  # all 57 eigenvalues, no slack
+    bound = 1e-10 + 64 * EPS * o['lam'][:, -1:] / o['lam']            # documented: scipy's own (LAPACK) error bound
+    assert (np.abs(lam / o['lam'] - 1) < bound).all()
+    phi = out['phi'].cpu().numpy()
     gap = np.minimum(np.diff(o['lam'], axis=1, prepend=-np.inf), np.diff(o['lam'], axis=1, append=np.inf))[:, :10]
     tol = 1e-10 + 256 * EPS * o['lam'][:, -1:] / gap
-    assert (util.mode_err(out['phi'].cpu().numpy(), o['phi']) < tol).all()
+    assert (util.mode_err(phi, o['phi'][:, :10]) < tol).all()
+    # eigenvectors without scipy in the loop: residual and M-orthonormality of the first 10 modes in extended precision
+    K, M = o['Kc'].astype(np.longdouble), o['Mc'].astype(np.longdouble)
+    V = phi[:, :, keep].astype(np.longdouble)
+    R = np.einsum('bij,bmj->bmi', K, V) - lam[:, :10, None] * np.einsum('bij,bmj->bmi', M, V)
+    scale = np.abs(o['Kc']).max(axis=(1, 2))[:, None] * np.abs(phi).max(axis=2)
+    assert (np.abs(R).max(axis=2).astype(np.float64) / scale).max() < 1e-13
+    G = np.einsum('bmi,bij,bnj->bmn', V, M, V).astype(np.float64)
+    assert np.abs(G - np.eye(10)).max() < 1e-10
 
 
 def test_modal_unfused_equals_fused():

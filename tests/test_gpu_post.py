@@ -64,6 +64,75 @@ def test_internal_actions_and_participation_vs_reference(case):
     assert np.abs(gam * sref - gref).max() / np.abs(gref).max() < 1e-8
 
 
+def beam_loads(model, nE, n_conc=2):
+    """uniform q_axial / q_perp [C, nE] and concentrated-load descriptors [C, nE, n_conc, 3] of a golden model"""
+    C = len(model['load_cases'])
+    qa, qp, conc = np.zeros((C, nE)), np.zeros((C, nE)), np.zeros((C, nE, n_conc, 3))
+    used = np.zeros((C, nE), dtype=int)
+    for c, lc in enumerate(model['load_cases']):
+        for bi, kind, kw in lc.get('beam', []):
+            if kind == 'uniform axial force':
+                qa[c, bi] += kw['value']
+            elif kind == 'uniform perpendicular force':
+                qp[c, bi] += kw['value']
+            else:
+                conc[c, bi, used[c, bi]] = (batch.LOAD_KINDS[kind], kw['value'], kw.get('position', 0.0))
+                used[c, bi] += 1
+    return qa, qp, conc
+
+
+@pytest.mark.parametrize('case', ['clamped_clamped_loads', 'vertical_beam', 'cantilever_example'])
+def test_concentrated_load_curves_vs_reference(case):
+    """N / V / M fields of beams carrying the three CONCENTRATED load types (Loads.py:347-365, 421-432,
+    489-502), against HermitianBeam2D.internal_action of the real reference at 11 positions (xi = 0.3, the load
+    position of two of the cases, is sampled exactly: the reference's comparisons at xi == position are pinned), and
+    the per-beam maxima, which must see the one-sided limits at the load positions."""
+    model = util.golden_models()[case]
+    pm = util.pack(model)
+    nN, nE = len(model['nodes']), len(model['beams'])
+    plan = Plan.from_supports(nN, pm['conn'], model['supports'], pm['lumped'])
+    out = batch.solve_fused(plan, T(pm['coords'][None]), T(pm['props'][None]), None, T(pm['f_nodal'][None]),
+                            T(pm['r_local'][None]), modal=False)
+    assert int(out['info'][0]) == 0
+    qa, qp, conc = beam_loads(model, nE)
+    act, mx = batch.internal_actions(plan, T(pm['coords'][None]), out['endforces'], T(qa[None]), T(qp[None]), npts=11,
+                                     conc=T(conc[None]))
+    ref = POST[case + '/internal_actions']                       # [C, nE, 3, 11]
+    got = act[0].cpu().numpy()
+    scale = np.maximum(np.abs(ref).max(axis=(1, 3), keepdims=True), 1e-300)
+    assert (np.abs(got - ref) / scale).max() < 1e-9
+    # maxima: at least the sampled ones; where a load sits between / on samples, the one-sided limits as well
+    mxn = mx[0].cpu().numpy()
+    assert (mxn >= np.abs(got).max(axis=-1) - 1e-12 * scale[..., 0]).all()
+    if case == 'clamped_clamped_loads':
+        # LC 2: P = -30 at 0.3 of a clamped-clamped beam: |V| jumps from 23.52 to 6.48 at the load; the moment kink
+        # under the load, M(0.3) = 441 - 23.52 * 30 = -264.6, is a sampled point; LC 3: M = -200 at 0.3: the moment
+        # line climbs 14 ... 89.6 and drops by 200 AT the load: the reference returns the left value there, the largest
+        # |M| = 110.4 is the right-hand limit, which only the one-sided evaluation sees
+        assert abs(mxn[1, 0, 1] - 23.52) < 1e-9 and abs(mxn[1, 0, 2] - 441.0) < 1e-9
+        left = ref[2, 0, 2, 3]                                    # reference value at xi = 0.3 (its `xi > pos` is False)
+        assert abs(mxn[2, 0, 2] - max(np.abs(ref[2, 0, 2]).max(), abs(left), abs(left + (-200)))) < 1e-9
+
+
+def test_concentrated_load_maxima_between_samples():
+    """A load position that no sample hits: the extreme shear / moment only shows in the one-sided limits."""
+    model = util.golden_models()['clamped_clamped_loads']
+    pm = util.pack(model)
+    plan = Plan.from_supports(2, pm['conn'], model['supports'], pm['lumped'])
+    # simply supported reading of the same beam: end forces of P at a = 0.37 on a pinned-pinned span are
+    # (V1, V2) = (b P, a P), M1 = M2 = 0; feed them directly
+    P, a, L = 10.0, 0.37, 100.0
+    ef = np.zeros((1, 1, 1, 6))
+    ef[0, 0, 0] = [0.0, (1 - a) * P, 0.0, 0.0, a * P, 0.0]
+    conc = np.zeros((1, 1, 1, 1, 3))
+    conc[0, 0, 0, 0] = (batch.LOAD_KINDS['concentrated perpendicular force'], -P, a)
+    act, mx = batch.internal_actions(plan, T(pm['coords'][None]), T(ef), None, None, npts=5, conc=T(conc))
+    got, mxn = act[0, 0, 0].cpu().numpy(), mx[0, 0, 0].cpu().numpy()
+    # the largest moment sits under the load: M = a b P L = 233.1 -- none of the 5 samples sees it
+    assert abs(mxn[2] - a * (1 - a) * P * L) < 1e-9 and np.abs(got[2]).max() < mxn[2] - 1.0
+    assert abs(mxn[1] - (1 - a) * P) < 1e-12
+
+
 def test_post_kernels_batch_vs_oracle():
     B = 2000
     P = sweep.p20_draw_params(B)
