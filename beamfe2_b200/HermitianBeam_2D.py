@@ -72,6 +72,22 @@ class HermitianBeam2D(object):
                                     t(0.0 if self.rho is None else self.rho), lump)   # rho is optional for static-only models
         return Kg[0].cpu().numpy(), Mg[0].cpu().numpy()
 
+    def _Ke_geom(self, N=-1):
+        """Geometric stiffness of the element for the axial force N (tension positive), local axes -- the consistent
+        matrix of the cubic Hermite shape functions (H.-P. Gavin, CEE 421L, the source HermitianBeam_2D.py:261-282
+        cites).  The reference's own transcription has sign slips in four entries ([1,4], [1,5], [5,5] and the missing
+        [1,5]) and its buckling solver is unfinished (README.md:27); this is the matrix it names.  The GPU path
+        assembles the same numbers in bfe2_assemble_geometric."""
+        L = self.l
+        a, b, c, d = 6. / 5., L / 10., 2. * L ** 2 / 15., -L ** 2 / 30.
+        k = np.zeros((6, 6))
+        k[np.ix_([1, 2, 4, 5], [1, 2, 4, 5])] = [[a, b, -a, b], [b, c, -b, d], [-a, -b, a, -b], [b, d, -b, c]]
+        return np.multiply(N / L, k)
+
+    @property
+    def Ke_geom(self):
+        return self._Ke_geom()
+
     @property
     def Ke(self):
         return self._k1(local=True)[0]

@@ -109,10 +109,47 @@ class ModalSolver(Solver):
 
 
 class BucklingSolver(Solver):
-    """Out of scope: the reference's buckling solver is unfinished (Solver.py:95-180 calls exit())."""
+    """Linear buckling.  The reference's solver (Solver.py:90-180) is unfinished -- it prints
+    debug output and calls exit() -- so the contract here is the one it sketches: run the linear static analysis for
+    the loads on the structure, build K_g from the axial forces it gives, solve (K + lambda K_g) phi = 0 on the
+    condensed matrices and store results['buckling'] = BucklingResult(criticals = the positive load factors in
+    ascending order, bucklingshapes = shapes re-expanded to all DOFs).  Returns False without loads."""
+
+    def __init__(self, structure=None):
+        super(BucklingSolver, self).__init__(structure)
+        self.nr_modes = 1
 
     def solve(self):
-        raise NotImplementedError('linear buckling is not part of the accelerated path')
+        import torch
+        from . import batch
+        st = self.structure
+        if st._load_vector is None or np.count_nonzero(st._load_vector) == 0:
+            return False
+        if not torch.cuda.is_available():
+            raise RuntimeError('beamfe2_b200 solvers need a CUDA device (no CPU fallback)')
+        plan, pk = st.pack()
+        if plan.n_free == 0 or plan.n_free > MAX_JACOBI_N:
+            raise NotImplementedError('buckling runs on the dense path: 1 <= n_free <= %d' % MAX_JACOBI_N)
+
+        def dev(a):
+            return torch.as_tensor(np.ascontiguousarray(a[None]), dtype=torch.float64, device='cuda')
+        nm = max(1, min(int(self.nr_modes), plan.n_free))
+        out = batch.buckling(plan, dev(pk['coords']), dev(pk['props']), dev(pk['f_nodal']), dev(pk['r_local']), n_modes=nm)
+        torch.cuda.synchronize()
+        info = int(out['info'][0].item())
+        if info > 0:
+            raise np.linalg.LinAlgError('stiffness matrix is singular (pivot %d)' % info)
+        if info != 0:
+            raise np.linalg.LinAlgError('buckling solve failed (info %d)' % info)
+        lf = out['load_factor'][0].cpu().numpy()
+        phi = out['phi'][0].cpu().numpy()
+        keep = np.isfinite(lf)
+        st.results['buckling'] = Results.BucklingResult(
+            structure=st, criticals=[float(x) for x in lf[keep]],
+            bucklingshapes=[np.matrix(phi[k]).T for k in range(phi.shape[0]) if keep[k]])
+        st.results['buckling'].solved = True
+        st.results['buckling'].axial_forces = out['axial'][0].cpu().numpy()
+        return True
 
 
 def solve_structures(structures, static=True, modal=True):

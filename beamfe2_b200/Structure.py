@@ -204,6 +204,12 @@ class Structure(object):
         return self._assemble_dense(False)[1]
 
     @property
+    def K_geom(self):
+        """compiled geometric stiffness with the reference's default N = -1 per beam (Structure.py:211-214)"""
+        from . import helpers
+        return helpers.compile_global_matrix(self.beams, geometrical=True)
+
+    @property
     def M_with_masses(self):
         if self._mass_vector is None:
             self._mass_vector = np.matrix(np.zeros(self.sumdof))

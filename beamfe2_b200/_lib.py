@@ -14,13 +14,13 @@ SYMBOLS = (
     'bfe2_plan_create', 'bfe2_plan_create_ex', 'bfe2_plan_destroy', 'bfe2_plan_dims', 'bfe2_plan_get_array',
     'bfe2_plan_smem_bytes', 'bfe2_workspace_bytes',
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
-    'bfe2_solve_fused',
+    'bfe2_solve_fused', 'bfe2_set_modal_engine', 'bfe2_get_modal_engine',
     'bfe2_pattern_create', 'bfe2_pattern_destroy', 'bfe2_pattern_layout', 'bfe2_solve_fused_packed',
     'bfe2_plan_create_dense', 'bfe2_sym_eig_dense',
     'bfe2_beam_create', 'bfe2_beam_create_ex', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve',
     'bfe2_beam_solve_dd', 'bfe2_beam_matvec', 'bfe2_beam_residual', 'bfe2_beam_export_blocks',
     'bfe2_gram_workspace_bytes', 'bfe2_gram64', 'bfe2_update64',
-    'bfe2_internal_actions', 'bfe2_internal_actions_ex', 'bfe2_modal_participation',
+    'bfe2_internal_actions', 'bfe2_internal_actions_ex', 'bfe2_modal_participation', 'bfe2_assemble_geometric',
 )
 
 ARR_CONN, ARR_FREE_OF_POS, ARR_POS_OF_FREE, ARR_FIXED, ARR_SLOT_PTR, ARR_CONTRIB, ARR_NODE_PTR, \
@@ -82,6 +82,9 @@ def lib():
     L.bfe2_modal_solve.argtypes = [vp, i64, i32] + [vp] * 7
     L.bfe2_solve_fused.restype = C.c_int
     L.bfe2_solve_fused.argtypes = [vp, i64, i32, i32, i32] + [vp] * 13
+    L.bfe2_set_modal_engine.restype = C.c_int
+    L.bfe2_set_modal_engine.argtypes = [i32]
+    L.bfe2_get_modal_engine.restype = C.c_int
     L.bfe2_pattern_create.restype = C.c_int
     L.bfe2_pattern_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32, i32, vp, i32, vp]
     L.bfe2_pattern_destroy.restype = None
@@ -122,6 +125,8 @@ def lib():
     L.bfe2_internal_actions.argtypes = [vp, i64, i32, i32] + [vp] * 7
     L.bfe2_internal_actions_ex.restype = C.c_int
     L.bfe2_internal_actions_ex.argtypes = [vp, i64, i32, i32] + [vp] * 4 + [i32] + [vp] * 4
+    L.bfe2_assemble_geometric.restype = C.c_int
+    L.bfe2_assemble_geometric.argtypes = [vp, i64, vp, vp, vp, vp]
     L.bfe2_modal_participation.restype = C.c_int
     L.bfe2_modal_participation.argtypes = [vp, i64, i32] + [vp] * 4
     _lib = L

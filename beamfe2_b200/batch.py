@@ -15,6 +15,19 @@ def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+MODAL_ENGINES = {'jacobi': 0, 'two_ended': 1}
+
+
+def set_modal_engine(name: str):
+    """Process-wide choice of the modal engine of the fused path (include/bfe2.h): 'jacobi' (default) = one-sided Jacobi
+    on the pivoted-Cholesky factor; 'two_ended' (n_free <= 64, n_modes <= 16) = tridiagonalisation of C and of C^-1 +
+    Sturm bisection + inverse iteration, with the Jacobi engine repairing what it declines.  Returns the previous name."""
+    L = _lib.lib()
+    prev = {v: k for k, v in MODAL_ENGINES.items()}[L.bfe2_get_modal_engine()]
+    _lib.check(L.bfe2_set_modal_engine(MODAL_ENGINES[name]))
+    return prev
+
+
 def _chk(t, shape, name, dtype=torch.float64):
     if t is None:
         return None
@@ -94,6 +107,105 @@ def modal_solve(plan: Plan, Kb, Mb, n_modes=None):
                                               _lib.ptr(lam), _lib.ptr(phi), _lib.ptr(info),
                                               _lib.ptr(sweeps), _stream_ptr()))
     return dict(lam=lam, phi=phi, info=info, sweeps=sweeps)
+
+
+def assemble_geometric(plan: Plan, coords, axial):
+    """Condensed band Kgb [B, hbw+1, n] of the geometric stiffness K_g(N) for axial forces axial [B, nE] (tension
+    positive; HermitianBeam_2D.py:261-282, Structure.py:211-214)."""
+    B = coords.shape[0]
+    coords = _chk(coords, (B, plan.n_nodes, 2), 'coords')
+    axial = _chk(axial, (B, plan.n_elem), 'axial')
+    Kgb = torch.empty((B, plan.hbw + 1, plan.n_free), dtype=torch.float64, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _lib.check(_lib.lib().bfe2_assemble_geometric(plan.handle, B, _lib.ptr(coords), _lib.ptr(axial), _lib.ptr(Kgb),
+                                                      _stream_ptr()))
+    return Kgb
+
+
+def buckling(plan: Plan, coords, props, f_nodal, r_local=None, n_modes=3, load_case=0):
+    """Linear buckling of a batch (the reference's BucklingSolver, Solver.py:90-180, is unfinished).
+
+    1. static solve for the reference loads -> axial forces N_e = endforces[.., e, 3] (tension positive);
+    2. K_g(N) assembled on the device (bfe2_assemble_geometric);
+    3. (K + lambda K_g) phi = 0  <=>  (-K_g) phi = mu K phi, mu = 1 / lambda.  Both passes run on the dense
+       Cholesky-reduction + Jacobi kernel (bfe2_modal_solve) with K -- positive definite -- in M's role:
+         pass 1 (eigenvalues only): (-K_g + s K, K), a small shift s making the left matrix definite -> mu_max, mu_min
+         pass 2: (K_g + sigma K, K) with sigma = 2 mu_max: its LOWEST eigenvalues theta = sigma - mu belong to the
+                 largest mu, i.e. to the smallest positive critical factors, and come with their shapes.
+    Returns dict(load_factor [B, n_modes] ascending (inf where fewer positive factors exist), phi [B, n_modes, sumdof]
+    (K-normalised: phi^T K phi = 1), axial [B, nE], info [B])."""
+    B = coords.shape[0]
+    dev = coords.device
+    n = plan.n_free
+    st = solve_fused(plan, coords, props, None, f_nodal, r_local, modal=False, want_reactions=False)
+    axial = st['endforces'][:, load_case, :, 3].contiguous()
+    Kb, _ = assemble_banded(plan, coords, props, None, want_mass=False)
+    Kg = assemble_geometric(plan, coords, axial)
+    info = st['info'].clone()
+    # scale of mu: |K_g| / |K| on the diagonals
+    ratio = (Kg[:, 0].abs().amax(dim=1) / Kb[:, 0].abs().amax(dim=1)).clamp_min(1e-300)
+    mu_max = torch.zeros(B, dtype=torch.float64, device=dev)
+    todo = info == 0
+    shift = 1e-9 * ratio
+    for _ in range(8):                                   # members in tension make -K_g indefinite: raise the shift
+        if not bool(todo.any()):
+            break
+        idx = torch.nonzero(todo).reshape(-1)
+        A = -Kg[idx] + shift[idx, None, None] * Kb[idx]
+        r = modal_solve(plan, A, Kb[idx], n_modes=0)
+        ok = r['info'] == 0
+        mu_max[idx[ok]] = r['lam'][ok, -1] - shift[idx[ok]]
+        todo[idx[ok]] = False
+        shift[idx[~ok]] *= 100.0
+    info[todo] = -2
+    good = (info == 0) & (mu_max > 0)                    # mu_max <= 0: nothing buckles under this load
+    lf = torch.full((B, n_modes), float('inf'), dtype=torch.float64, device=dev)
+    phi = torch.zeros((B, n_modes, plan.sumdof), dtype=torch.float64, device=dev)
+    if bool(good.any()):
+        idx = torch.nonzero(good).reshape(-1)
+        sigma = 2.0 * mu_max[idx]
+        A = Kg[idx] + sigma[:, None, None] * Kb[idx]
+        r = modal_solve(plan, A, Kb[idx], n_modes=n_modes)
+        mu = sigma[:, None] - r['lam'][:, :n_modes]
+        lf[idx] = torch.where(mu > 0, 1.0 / mu.clamp_min(1e-300), torch.full_like(mu, float('inf')))
+        phi[idx] = r['phi']
+        bad = r['info'] != 0
+        info[idx[bad]] = r['info'][bad]
+    return dict(load_factor=lf, phi=phi, axial=axial, info=info)
+
+
+def modal_lumped_condensed(plan: Plan, coords, props, nodal_mass=None, n_modes=None):
+    """Lumped-mass modal analysis WITHOUT the reference's m * 1e-10 rotary terms (HermitianBeam_2D.py:225-231, which make
+    cond(M) ~ 1e10 and produce negative eigenvalues): the rotations are massless, M is positive
+    SEMI-definite, and the pencil is solved the other way round, M phi = mu K phi (mu = 1 / lam, K positive definite in
+    M's role) -- mathematically the static (Guyan) condensation of the massless rotations, which is exact here.  The
+    n_t = number of free translations finite modes come out with mu > 0; the massless directions have mu = 0 exactly
+    (lam = inf) and are dropped.  `plan` must have been created with every beam flagged lumped.
+    Returns dict(lam [B, n_t] ascending, phi [B, n_modes, sumdof] M-normalised, n_t, info)."""
+    B = coords.shape[0]
+    n = plan.n_free
+    assert plan.lumped is not None and bool(plan.lumped.all()), 'every beam must use the lumped mass matrix'
+    Kb, Mb = assemble_banded(plan, coords, props, nodal_mass)
+    pos = torch.as_tensor(plan.pos_of_free.astype('int64'), device=coords.device)
+    rot = (pos % 3) == 2
+    Mb = Mb.clone()
+    Mb[:, 0, rot] = 0.0                                  # exactly massless rotations
+    n_t = int((~rot).sum().item())
+    n_modes = n_t if n_modes is None else min(int(n_modes), n_t)
+    # shift s: M + s K is positive definite and (M + s K) phi = (mu + s) K phi EXACTLY, so s costs no accuracy; it only
+    # has to keep the 30-odd massless directions (mu = 0) above the pivot test of the kernel, i.e. s ~ 1e-9 mu_max.
+    # mu_max is estimated by one step of the power iteration x = K^-1 M 1 (one launch of the static kernel):
+    # mu_est = x^T M x / x^T K x <= mu_max, and close to it for this smooth start vector.
+    mdiag = torch.zeros((B, 1, plan.sumdof), dtype=torch.float64, device=coords.device)
+    mdiag[:, 0, pos] = Mb[:, 0]
+    x = static_solve(plan, Kb, coords, props, mdiag, None, want_endforces=False, want_reactions=False)['u'][:, 0]
+    mu_est = (mdiag[:, 0] * x * x).sum(dim=1) / (mdiag[:, 0] * x).sum(dim=1)
+    shift = 1e-9 * mu_est
+    r = modal_solve(plan, Mb + shift[:, None, None] * Kb, Kb, n_modes=n)     # ascending theta = mu + s, all shapes
+    mu = (r['lam'] - shift[:, None]).flip(1)[:, :n_t]    # descending mu = ascending lam
+    lam = 1.0 / mu
+    phi = r['phi'].flip(1)[:, :n_modes] / torch.sqrt(mu[:, :n_modes])[:, :, None]   # phi^T K phi = 1 -> phi^T M phi = 1
+    return dict(lam=lam, phi=phi.contiguous(), n_t=n_t, info=r['info'])
 
 
 def solve_fused(plan: Plan, coords, props, nodal_mass=None, f_nodal=None, r_local=None, modal=True,

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,7 +27,7 @@ using namespace bfe2;
 // anonymous namespace, so each unit instantiates only what its entry points launch.
 int bfe2_fail(int code, const char* fmt, ...);
 
-#ifndef BFE2_TU_PACKED
+#if !defined(BFE2_TU_PACKED) && !defined(BFE2_TU_TE)
 namespace {
 thread_local std::string g_err = "";
 
@@ -195,7 +196,7 @@ int plan_upload(bfe2_plan* p, PlanDev* out) {
 }  // namespace
 
 // shared with bfe2_post.cu: device view of a plan on the current device (uploads lazily); < 0 + last_error on failure
-#ifndef BFE2_TU_PACKED
+#if !defined(BFE2_TU_PACKED) && !defined(BFE2_TU_TE)
 int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out) { return plan_upload(plan, out); }
 #else
 int bfe2_plan_device_view(bfe2_plan* plan, PlanDev* out);
@@ -220,6 +221,9 @@ struct BatchArgs {
     // [C, sumdof] and [C, nE, 6]); compact_out: u and phi on the n free DOFs, reactions at the n_fixed supported ones.
     int w_in, w_out, compact_in, compact_out, nnz_f, nnz_r, n_fixed;
     const int32_t *f_idx, *r_idx, *fixed_pos;
+    // only_flagged: this launch repairs an earlier one -- a block whose structure does not carry info ==
+    // BFE2_INFO_RETRY (the two-ended modal engine declined it) leaves at once
+    int only_flagged;
 };
 
 __device__ __forceinline__ void copy_in(double* dst, const double* src, int count, int tid, int nt) {
@@ -813,6 +817,7 @@ k_solve(PlanDev P, BatchArgs A) {
     const int n = P.n;
     int* s_order = reinterpret_cast<int*>(smem + L.order);
     int* s_flag = s_order + P.npad;                  // [0] = K cholesky info, [1] = M cholesky info
+    if (A.only_flagged && A.info[b * ((PACKED && A.w_out) ? 2LL * A.w_out : 1LL)] != BFE2_INFO_RETRY) return;
 
     // per-structure strides (doubles): natural sizes of the dense tensors, or the record widths when packed.  The
     // output addresses are formed where they are used (after the sweeps), so nothing extra stays live across them.
@@ -1104,12 +1109,173 @@ int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaS
 
 }  // namespace
 
+// ---- two-ended modal engine (bfe2_te.cuh; compiled in its own translation unit, bfe2_te_tu.cu) ---------------
+// bfe2_te_launch: plan / PlanDev / BatchArgs pass as untyped pointers because BatchArgs lives in this file's anonymous
+// namespace (every unit compiles the same text).  Returns 0 (launched), 1 (not eligible: nothing launched), < 0.
+int bfe2_te_launch(bfe2_plan* plan, const void* plan_dev, const void* batch_args, void* stream, int packed);
+extern "C" int bfe2_get_modal_engine(void);
+
+namespace {
+[[maybe_unused]] inline bool te_wanted(const bfe2_plan* plan, const BatchArgs& A) {
+    return A.do_modal && plan->nE > 0 && plan->n >= 3 && plan->n <= 64 && A.n_modes <= 16 && plan->hbw < plan->n &&
+           bfe2_get_modal_engine() == BFE2_ENGINE_TWO_ENDED;
+}
+}  // namespace
+
+#ifdef BFE2_TU_TE
+#include "bfe2_te.cuh"
+namespace {
+
+struct TeLayout {
+    int coords, props, mass, geo, Kb, Mb, invK, invM, te, total, LD;
+};
+__host__ __device__ inline TeLayout make_te_layout(int nN, int nE, int n, int hbw, int C, int n_modes) {
+    TeLayout L;
+    int o = 0;
+    L.coords = o; o += 2 * nN;
+    L.props = o;  o += 4 * nE;
+    L.mass = o;   o += 2 * nN;
+    L.geo = o;    o += 3 * nE;
+    L.Kb = o;     o += (hbw + 1) * n;
+    L.Mb = o;     o += (hbw + 1) * n;
+    L.invK = o;   o += n;
+    L.invM = o;   o += n;
+    o = (o + 1) & ~1;
+    L.te = o;
+    L.LD = n | 1;
+    // region `te` is a union: beam numbers (elements / assembly), the modal block, the static stage
+    o += imax3((K7_PITCH + M12_PITCH) * nE, te::smem_layout(n, L.LD, n_modes).total, C * (n + 6 * nN + 12 * nE));
+    L.total = o;
+    return L;
+}
+
+// fused K1 -> K4 with the two-ended modal engine: one block of 64 threads per structure
+template <int N, bool PACKED>
+__global__ void __launch_bounds__(64, 5)
+k_solve_te(PlanDev P, BatchArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const TeLayout L = make_te_layout(P.nN, P.nE, P.n, P.hbw, A.C, A.n_modes);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long long b = blockIdx.x;
+    const int n = P.n;
+    const long long in_w = PACKED ? A.w_in : 0, out_w = PACKED ? A.w_out : 0;
+    const bool compact_out = PACKED && A.compact_out;
+    const int nu = compact_out ? n : P.sumdof, nre = compact_out ? A.n_fixed : P.sumdof;
+    double* g_u = A.u ? A.u + b * (out_w ? out_w : (long long)A.C * nu) : nullptr;
+    double* g_ef = A.endforces ? A.endforces + b * (out_w ? out_w : (long long)A.C * P.nE * 6) : nullptr;
+    double* g_re = A.reactions ? A.reactions + b * (out_w ? out_w : (long long)A.C * nre) : nullptr;
+    double* g_lam = A.lam + b * (out_w ? out_w : (long long)n);
+    double* g_phi = A.phi ? A.phi + b * (out_w ? out_w : (long long)A.n_modes * nu) : nullptr;
+    int32_t* g_info = A.info + b * (out_w ? 2 * out_w : 1);
+    int32_t* g_sweeps = A.sweeps ? A.sweeps + b * (out_w ? 2 * out_w : 1) : nullptr;
+
+    copy_in(smem + L.coords, A.coords + b * (in_w ? in_w : 2LL * P.nN), 2 * P.nN, tid, nt);
+    copy_in(smem + L.props, A.props + b * (in_w ? in_w : 4LL * P.nE), 4 * P.nE, tid, nt);
+    if (A.nodal_mass != nullptr) copy_in(smem + L.mass, A.nodal_mass + b * (in_w ? in_w : 2LL * P.nN), 2 * P.nN, tid, nt);
+    __syncthreads();
+    double* base = smem + L.te;
+    stage_elements_cf(P, smem + L.coords, smem + L.props, smem + L.geo, base, base + K7_PITCH * P.nE, true, tid, nt);
+    __syncthreads();
+    stage_assemble_cf(P, base, base + K7_PITCH * P.nE, A.nodal_mass ? smem + L.mass : nullptr, smem + L.Kb, smem + L.Mb,
+                      true, tid, nt);
+    __syncthreads();
+    const te::Smem S = te::smem_layout(n, L.LD, A.n_modes);
+    TeCtx ctx{tid, base + S.red, 0};
+    int info_k = 0;
+    const int rc = te::modal_block<N>(ctx, n, P.hbw, smem + L.Kb, smem + L.Mb, smem + L.invK, smem + L.invM, base, L.LD,
+                                      A.n_modes, &info_k);
+    if (rc > 0 || rc == BFE2_INFO_RETRY) {
+        // K not positive definite: every output is NaN.  Engine declined: the Jacobi launch that follows redoes the
+        // whole structure; leave NaNs so that a missing repair cannot go unnoticed.
+        if (tid == 0) {
+            *g_info = rc;
+            if (g_sweeps) *g_sweeps = 0;
+        }
+        if (A.do_static) {
+            fill_nan(g_u, (long long)A.C * nu, tid, nt);
+            fill_nan(g_ef, (long long)A.C * P.nE * 6, tid, nt);
+            fill_nan(g_re, (long long)A.C * nre, tid, nt);
+        }
+        fill_nan(g_lam, n, tid, nt);
+        fill_nan(g_phi, (long long)A.n_modes * nu, tid, nt);
+        return;
+    }
+    if (rc == -1) {                                   // mass matrix not positive definite: modal outputs NaN, static valid
+        fill_nan(g_lam, n, tid, nt);
+        fill_nan(g_phi, (long long)A.n_modes * nu, tid, nt);
+    } else {
+        for (int j = tid; j < n; j += nt) g_lam[j] = base[S.lam + j];
+        const double* Z = base + S.Z;
+        if (g_phi != nullptr) {
+            if (compact_out) {
+                for (int t = tid; t < A.n_modes * n; t += nt) g_phi[t] = Z[(t / n) * te::NT + t % n];
+            } else {
+                for (int t = tid; t < A.n_modes * P.sumdof; t += nt) {
+                    const int m = t / P.sumdof, j = P.free_of_pos[t % P.sumdof];
+                    g_phi[t] = (j >= 0) ? Z[m * te::NT + j] : 0.0;
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        *g_info = rc;                                 // 0 or -1
+        if (g_sweeps) *g_sweeps = 0;                  // no Jacobi sweeps in this engine
+    }
+    if (!A.do_static) return;
+    __syncthreads();                                  // region `te` becomes the static stage's scratch
+    double* s_f = base;
+    double* s_ufull = s_f + A.C * n;
+    double* s_ef = s_ufull + A.C * P.sumdof;
+    const double* fn = A.f_nodal + b * (in_w ? in_w : (long long)A.C * P.sumdof);
+    const double* rl = A.r_local ? A.r_local + b * (in_w ? in_w : (long long)A.C * P.nE * 6) : nullptr;
+    if (PACKED && A.compact_in) {
+        double* s_fd = s_ef + A.C * P.nE * 6;
+        double* s_rd = s_fd + A.C * P.sumdof;
+        const int nd = A.C * (P.sumdof + 6 * P.nE);
+        for (int i = tid; i < nd; i += nt) s_fd[i] = 0.0;
+        __syncthreads();
+        for (int i = tid; i < A.nnz_f; i += nt) s_fd[A.f_idx[i]] = fn[i];
+        for (int i = tid; i < A.nnz_r; i += nt) s_rd[A.r_idx[i]] = rl[i];
+        __syncthreads();
+        fn = s_fd;
+        rl = A.nnz_r > 0 ? s_rd : nullptr;
+    }
+    stage_static(P, A.C, smem + L.props, smem + L.geo, smem + L.Kb, smem + L.invK, s_f, s_ufull, s_ef, fn, rl, g_u, g_ef,
+                 g_re, tid, nt, true, compact_out ? A.fixed_pos : nullptr, A.n_fixed);
+}
+
+template <int N, bool PACKED>
+int launch_te(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
+    const TeLayout L = make_te_layout(plan->nN, plan->nE, plan->n, plan->hbw, A.C, A.n_modes);
+    const size_t bytes = (size_t)L.total * sizeof(double);
+    if (bytes > 227 * 1024) return 1;
+    auto kern = k_solve_te<N, PACKED>;
+    BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (A.B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
+    kern<<<(unsigned)A.B, 64, bytes, stream>>>(pd, A);
+    BFE2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int bfe2_te_launch(bfe2_plan* plan, const void* plan_dev, const void* batch_args, void* stream, int packed) {
+    const PlanDev& pd = *static_cast<const PlanDev*>(plan_dev);
+    const BatchArgs& A = *static_cast<const BatchArgs*>(batch_args);
+    if (!te_wanted(plan, A)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->n <= 32) return packed ? launch_te<32, true>(plan, pd, A, st) : launch_te<32, false>(plan, pd, A, st);
+    if (plan->n <= 58) return packed ? launch_te<58, true>(plan, pd, A, st) : launch_te<58, false>(plan, pd, A, st);
+    return packed ? launch_te<64, true>(plan, pd, A, st) : launch_te<64, false>(plan, pd, A, st);
+}
+#endif  // BFE2_TU_TE
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
 extern "C" {
 
-#ifndef BFE2_TU_PACKED
+#if !defined(BFE2_TU_PACKED) && !defined(BFE2_TU_TE)
 int bfe2_version(void) { return BFE2_VERSION; }
 
 const char* bfe2_last_error(void) { return g_err.c_str(); }
@@ -1419,8 +1585,20 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         BFE2_CUDA(cudaGetLastError());
         return 0;
     }
+    // two-ended engine selected (and n_free <= 64, few shapes wanted): it runs first; the Jacobi engine then only
+    // repairs the structures that engine declined (blocks of the others leave at once)
+    if (const int r = bfe2_te_launch(plan, &pd, &A, stream, 0); r < 0) return r;
+    else if (r == 0) A.only_flagged = 1;
     return dispatch_solve<true>(plan, pd, A, (cudaStream_t)stream);
 }
+
+static std::atomic<int> g_engine{BFE2_ENGINE_JACOBI};
+int bfe2_set_modal_engine(int32_t engine) {
+    if (engine != BFE2_ENGINE_JACOBI && engine != BFE2_ENGINE_TWO_ENDED) return fail(-1, "unknown modal engine %d", engine);
+    g_engine.store(engine);
+    return 0;
+}
+int bfe2_get_modal_engine(void) { return g_engine.load(); }
 
 #endif  // !BFE2_TU_PACKED
 
@@ -1550,12 +1728,14 @@ int bfe2_solve_fused_packed(bfe2_plan* plan, bfe2_pattern* q, int64_t B, const d
         BFE2_CUDA(cudaGetLastError());
         return 0;
     }
+    if (const int r = bfe2_te_launch(plan, &pd, &A, stream, 1); r < 0) return r;
+    else if (r == 0) A.only_flagged = 1;
     return dispatch_solve<true, true>(plan, pd, A, (cudaStream_t)stream);
 }
 
 #endif  // BFE2_TU_PACKED
 
-#ifndef BFE2_TU_PACKED
+#if !defined(BFE2_TU_PACKED) && !defined(BFE2_TU_TE)
 // ---- small dense generalized symmetric eigenproblem A q = theta B q (Rayleigh-Ritz step of the subspace
 //      iteration): the same Cholesky-reduction + Jacobi kernel on a synthetic "plan" with identity maps ---
 int bfe2_plan_create_dense(bfe2_plan** out, int32_t n) {

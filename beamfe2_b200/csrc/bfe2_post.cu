@@ -126,9 +126,72 @@ __global__ void k_participation(PlanDev P, long long B, int n_modes, const doubl
     gamma[t * 2 + 1] = gy;
 }
 
+// ---- geometric stiffness: banded assembly of K_g(N) for given axial forces ---------------
+// Local matrix of a beam with axial force N (tension positive), DOF order [ux_i, uy_i, rz_i, ux_j, uy_j, rz_j]:
+//   N/L * [ 6/5, L/10, -6/5, L/10 ; L/10, 2L^2/15, -L/10, -L^2/30 ; -6/5, -L/10, 6/5, -L/10 ; L/10, -L^2/30, -L/10, 2L^2/15 ]
+// on the (uy_i, rz_i, uy_j, rz_j) rows / columns, zero on the axial ones (the consistent matrix of the cubic Hermite
+// shape functions; H.-P. Gavin, CEE 421L, which HermitianBeam_2D.py:261-282 cites -- the reference's own transcription
+// has sign slips in four entries and its solver is unfinished, README.md:27; this is the matrix it names).
+__device__ __forceinline__ double kg_local(int a, int b, double g, double L) {
+    if (a == 0 || a == 3 || b == 0 || b == 3) return 0.0;
+    const bool ta = (a == 1 || a == 4), tb = (b == 1 || b == 4);       // translation (uy) or rotation
+    const bool ja = a >= 3, jb = b >= 3;                               // end j
+    if (ta && tb) return (ja == jb ? 1.2 : -1.2) * g;
+    if (ta != tb) {                                                    // uy - rz coupling: +L/10 from uy_i, -L/10 from uy_j
+        const bool tj = ta ? ja : jb;                                  // the end of the translation
+        return (tj ? -0.1 : 0.1) * g * L;
+    }
+    return (ja == jb ? 2.0 / 15.0 : -1.0 / 30.0) * g * L * L;
+}
+
+// thread per (structure, band slot); contributions are added in beam-list order like every other assembly here
+__global__ void k_assemble_geometric(PlanDev P, long long B, const double* __restrict__ coords,
+                                     const double* __restrict__ axial, double* __restrict__ Kgb) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * P.nslots) return;
+    const long long b = t / P.nslots;
+    const int slot = (int)(t % P.nslots);
+    const double* xy = coords + b * 2 * P.nN;
+    double acc = 0.0;
+    for (int p = P.slot_ptr[slot]; p < P.slot_ptr[slot + 1]; ++p) {
+        const int cbt = P.contrib[p];
+        const int e = cbt / 36, r = (cbt % 36) / 6, c = cbt % 6;
+        const int ni = P.conn[2 * e], nj = P.conn[2 * e + 1];
+        double L, cs, sn;
+        beam_geometry(xy[2 * ni], xy[2 * ni + 1], xy[2 * nj], xy[2 * nj + 1], L, cs, sn);
+        const double g = axial[b * P.nE + e] / L;
+        // (T kl T^T)[r][c] = sum_{a in block(r), d in block(c)} R[r][a] kl[a][d] R[c][d],  R = [[cs,-sn,0],[sn,cs,0],[0,0,1]]
+        const int r0 = 3 * (r / 3), c0 = 3 * (c / 3);
+        const double Rr[3] = {r % 3 == 0 ? cs : (r % 3 == 1 ? sn : 0.0), r % 3 == 0 ? -sn : (r % 3 == 1 ? cs : 0.0),
+                              r % 3 == 2 ? 1.0 : 0.0};
+        const double Rc[3] = {c % 3 == 0 ? cs : (c % 3 == 1 ? sn : 0.0), c % 3 == 0 ? -sn : (c % 3 == 1 ? cs : 0.0),
+                              c % 3 == 2 ? 1.0 : 0.0};
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) v += Rr[a] * kg_local(r0 + a, c0 + d, g, L) * Rc[d];
+        acc += v;
+    }
+    Kgb[t] = acc;
+}
+
 }  // namespace
 
 extern "C" {
+
+int bfe2_assemble_geometric(bfe2_plan* plan, int64_t B, const double* coords, const double* axial, double* Kgb,
+                            void* stream) {
+    if (plan && B == 0) return 0;
+    if (!plan || B < 0 || !coords || !axial || !Kgb) return bfe2_fail(-1, "bfe2_assemble_geometric: bad argument");
+    PlanDev pd;
+    if (const int r = bfe2_plan_device_view(plan, &pd)) return r;
+    const long long total = B * pd.nslots;
+    k_assemble_geometric<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(pd, B, coords, axial, Kgb);
+    if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_assemble_geometric launch failed");
+    return 0;
+}
+
 
 int bfe2_internal_actions_ex(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts, const double* coords,
                              const double* endforces, const double* q_axial, const double* q_perp, int32_t n_conc,

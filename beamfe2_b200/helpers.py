@@ -11,8 +11,6 @@ def compile_global_matrix(beams, stiffness=False, mass=False, geometrical=False)
     """Dense global K (stiffness=True) or M (mass=True) of a list of drop-in beams, assembled on the GPU in
     beam-list order with the block positions (ID - 1) * 3 of the reference."""
     assert stiffness or mass or geometrical
-    if geometrical and not (stiffness or mass):
-        raise NotImplementedError('geometric stiffness belongs to the (unfinished) buckling path: out of scope')
     import torch
     from . import batch
     from .plan import Plan
@@ -27,6 +25,11 @@ def compile_global_matrix(beams, stiffness=False, mass=False, geometrical=False)
         return torch.as_tensor(np.ascontiguousarray(a)[None], dtype=torch.float64, device='cuda')
     coords = dev([[float(n.x), float(n.y)] for n in nodes])
     props = dev([[float(b.E), float(b.A), float(b.I), float(b.rho if b.rho is not None else 0.0)] for b in beams])
+    if geometrical and not (stiffness or mass):
+        # helpers.py:26-27 sums b.Ke_geom, i.e. _Ke_geom() with its default N = -1 for every beam
+        axial = torch.full((1, len(beams)), -1.0, dtype=torch.float64, device='cuda')
+        band = batch.assemble_geometric(plan, coords, axial)[0].cpu().numpy()
+        return np.matrix(plan.band_to_dense(band))
     Kb, Mb = batch.assemble_banded(plan, coords, props, None, want_mass=bool(mass))
     torch.cuda.synchronize()
     band = (Kb if stiffness else Mb)[0].cpu().numpy()

@@ -274,6 +274,7 @@ def run_gpu_arm(args):
     dev = torch.device('cuda', local)
     numa = bdist.bind_to_gpu_numa_node(local) if world > 1 else None
     B = args.batch
+    batch.set_modal_engine(args.engine)
     conn, sup = sweep.p20_topology()
     plan = Plan.from_supports(21, conn, sup)
     P = sweep.p20_draw_params(B, shard=None if world == 1 else rank)
@@ -313,8 +314,9 @@ def run_gpu_arm(args):
     # ---- e2e: host buffers through the public HostPipeline API (packed records, compact load / result layouts)
     io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=N_MODES)
     pipe = batch.HostPipeline(plan, N_LC, N_MODES, chunk=args.chunk, n_streams=3, device=dev, io=io)
-    h_in, h_out = pipe.alloc_host(B)
-    io.pack_inputs(h_in, *[pk[k].cpu() for k in ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')])
+    Be = min(B, args.e2e_batch)                 # bounds the pinned host memory of a rank (11.1 KB per structure)
+    h_in, h_out = pipe.alloc_host(Be)
+    io.pack_inputs(h_in, *[pk[k][:Be].cpu() for k in ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local')])
     for _ in range(2):
         pipe.run(h_in, h_out)
     bdist.barrier()
@@ -330,15 +332,15 @@ def run_gpu_arm(args):
     e2e_ms = bdist.max_over_ranks(f0.elapsed_time(f1), dev) / e2e_steps
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
     bi, bo = pipe.bytes_per_structure()
-    e2e_value = B * world / (e2e_ms * 1e-3)
+    e2e_value = Be * world / (e2e_ms * 1e-3)
     hv = io.out_views(h_out)
     pos = torch.as_tensor(plan.pos_of_free.astype('int64'))
     fixed = torch.as_tensor(plan.fixed.astype('int64'))
-    e2e_ok = bool(torch.equal(hv['lam'], out['lam'].cpu()) and torch.equal(hv['u'], out['u'].cpu()[:, :, pos])
-                  and torch.equal(hv['phi'], out['phi'].cpu()[:, :, pos])
-                  and torch.equal(hv['endforces'], out['endforces'].cpu())
-                  and torch.equal(hv['reactions'], out['reactions'].cpu()[:, :, fixed])
-                  and torch.equal(hv['info'], out['info'].cpu()))
+    e2e_ok = bool(torch.equal(hv['lam'], out['lam'][:Be].cpu()) and torch.equal(hv['u'], out['u'][:Be].cpu()[:, :, pos])
+                  and torch.equal(hv['phi'], out['phi'][:Be].cpu()[:, :, pos])
+                  and torch.equal(hv['endforces'], out['endforces'][:Be].cpu())
+                  and torch.equal(hv['reactions'], out['reactions'][:Be].cpu()[:, :, fixed])
+                  and torch.equal(hv['info'], out['info'][:Be].cpu()))
 
     # ---- final gather of summaries (off the timed path)
     table = bdist.gather_summaries(bdist.summarize(out['u'], out['lam'], out['info']), B * world)
@@ -371,7 +373,8 @@ def run_gpu_arm(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, per_gpu=B),
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': bi * B, 'd2h_bytes_per_step': bo * B,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': bi * Be, 'd2h_bytes_per_step': bo * Be,
+                'structures_per_gpu_per_step': Be,
                 'ms_per_step': e2e_ms, 'wall_ms_per_step': e2e_wall * 1e3, 'chunk': args.chunk,
                 'copies_per_chunk': 2, 'layout': 'packed records: non-zero load entries in (%d of %d doubles), u / phi '
                 'on the free DOFs and reactions at the supports out' % (io.w_in, 713),
@@ -406,10 +409,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=100000, help='structure variants per GPU per step')
     ap.add_argument('--chunk', type=int, default=3125, help='HostPipeline chunk (structures)')
+    ap.add_argument('--e2e-batch', type=int, default=200000, help='end-to-end arm: at most this many structures per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=16384, help='CPU oracle: variants per worker')
     ap.add_argument('--ref-sample', type=int, default=256, help='real reference (arm A): variants in total')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--engine', default='jacobi', choices=['jacobi', 'two_ended'], help='modal engine of the fused path')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)

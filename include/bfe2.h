@@ -19,6 +19,8 @@
  *             == the reference's "stiffness matrix is singular" (Structure.py:325-354)
  *        -1  condensed mass matrix not positive definite / all-zero (Solver.py:34-35 returns False)
  *        -2  Jacobi did not converge in BFE2_MAX_SWEEPS sweeps / the reduced matrix broke down
+ *        -3  (BFE2_INFO_RETRY) internal: the two-ended modal engine declined the structure; the Jacobi engine
+ *            repairs it inside the same call, so a caller never sees this value
  *     k > 0 invalidates every output of that structure (NaN).  -1 / -2 invalidate only the MODAL outputs
  *     (lam, phi = NaN): K factored fine, so u / endforces / reactions of that structure are valid.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with -100.
@@ -137,6 +139,21 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
                      double* u, double* endforces, double* reactions,
                      double* lam, double* phi, int32_t* info, int32_t* sweeps, void* stream);
 
+/* ---- modal engine of the fused path (process-wide setting):
+ *      BFE2_ENGINE_JACOBI     (default) one-sided Jacobi on the pivoted-Cholesky factor, any n_free <= BFE2_MAX_JACOBI_N
+ *      BFE2_ENGINE_TWO_ENDED  for n_free <= 64 and n_modes <= 16: Householder tridiagonalisation of C = Lm^-1 K Lm^-T
+ *                             AND of C^-1, Sturm bisection -- every eigenvalue from the end of the spectrum it is
+ *                             closer to, so the small ones keep their relative accuracy, which the plain LAPACK route
+ *                             (scipy's dsygvd included) does not --, inverse iteration + back-transformation for the
+ *                             shapes (bfe2_te.cuh); a structure it declines is repaired by the Jacobi engine in the same
+ *                             call.  Both engines meet the 1e-10 bar against the 40-digit truth fixture; on B200 the
+ *                             Jacobi engine is 2.5x faster at n_free = 57 (profiles/r2_te_engine.md), hence the default. */
+#define BFE2_ENGINE_JACOBI    0
+#define BFE2_ENGINE_TWO_ENDED 1
+#define BFE2_INFO_RETRY   (-3)
+int bfe2_set_modal_engine(int32_t engine);
+int bfe2_get_modal_engine(void);
+
 /* ---- the same fused path on PACKED RECORDS with compact load / result layouts: the end-to-end entry for data
  *      that lives in HOST memory (one copy per direction per chunk; only numbers that carry information travel).
  *      A pattern is created once per (plan, load layout):
@@ -233,6 +250,14 @@ int bfe2_internal_actions_ex(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts
                              double* actions, double* maxabs, void* stream);
 int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,
                              double* gamma, void* stream);
+
+/* ---- geometric stiffness and linear buckling (HermitianBeam_2D.py:261-282 _Ke_geom,
+ *      Structure.py:211-214 K_geom, helpers.py:22-27 geometrical branch, Solver.py:90-180 BucklingSolver -- unfinished
+ *      in the reference, README.md:27).  Kgb [B, hbw+1, n]: condensed band of K_g for the axial forces
+ *      axial [B, nE] (tension positive; the static end forces give N_e = endforces[.., e, 3]).  The buckling pencil
+ *      (K + lambda K_g) phi = 0 is solved with bfe2_modal_solve on (K_g + sigma K, K): see beamfe2_b200/batch.py. */
+int bfe2_assemble_geometric(bfe2_plan* plan, int64_t B, const double* coords, const double* axial, double* Kgb,
+                            void* stream);
 
 #ifdef __cplusplus
 }
