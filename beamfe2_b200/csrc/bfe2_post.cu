@@ -176,9 +176,33 @@ __global__ void k_assemble_geometric(PlanDev P, long long B, const double* __res
     Kgb[t] = acc;
 }
 
+// symmetric band matrix (lower band, [hbw+1][n]: band[d][j] = A[j+d][j]) times a multi-vector X [n, nrhs] (row-major):
+// thread per (row, column); used by the first-k modal route of large frames (K X, M X of the subspace iteration)
+__global__ void k_band_matvec(int n, int hbw, int nrhs, const double* __restrict__ band, const double* __restrict__ X,
+                              double* __restrict__ Y) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * nrhs) return;
+    const int i = (int)(t / nrhs), r = (int)(t % nrhs);
+    double acc = band[i] * X[t];
+    for (int d = 1; d <= hbw; ++d) {
+        if (i + d < n) acc = fma(band[d * n + i], X[(long long)(i + d) * nrhs + r], acc);          // A[i+d][i] x[i+d]
+        if (i - d >= 0) acc = fma(band[d * n + i - d], X[(long long)(i - d) * nrhs + r], acc);      // A[i][i-d] x[i-d]
+    }
+    Y[t] = acc;
+}
+
 }  // namespace
 
 extern "C" {
+
+int bfe2_band_matvec(int32_t n, int32_t hbw, int32_t nrhs, const double* band, const double* X, double* Y, void* stream) {
+    if (n < 1 || hbw < 0 || nrhs < 1 || !band || !X || !Y || X == Y) return bfe2_fail(-1, "bfe2_band_matvec: bad argument");
+    const long long total = (long long)n * nrhs;
+    k_band_matvec<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, hbw, nrhs, band, X, Y);
+    if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_band_matvec launch failed");
+    return 0;
+}
+
 
 int bfe2_assemble_geometric(bfe2_plan* plan, int64_t B, const double* coords, const double* axial, double* Kgb,
                             void* stream) {

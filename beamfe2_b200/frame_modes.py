@@ -29,7 +29,7 @@ class FrameModes(SubspaceIteration):
         c1, p1 = coords.reshape(1, plan.n_nodes, 2).contiguous(), props.reshape(1, plan.n_elem, 4).contiguous()
         m1 = None if nodal_mass is None else nodal_mass.reshape(1, plan.n_nodes, 2).contiguous()
         Kb, Mb = batch.assemble_banded(plan, c1, p1, m1)
-        self.Kb, self.Mb = Kb[0], Mb[0]                               # [hbw + 1, n]
+        self.Kb, self.Mb = Kb[0].contiguous(), Mb[0].contiguous()     # [hbw + 1, n]
         # the Q right-hand sides of one K^-1 application are Q "structures" with the same band and geometry
         self._Kb_rep = Kb.expand(Q, -1, -1).contiguous()
         self._c_rep = c1.expand(Q, -1, -1).contiguous()
@@ -55,21 +55,21 @@ class FrameModes(SubspaceIteration):
         return out
 
     def matvec(self, X, mass=False, out=None):
-        """K X or M X from the band (lower diagonals d = 0..hbw of the symmetric matrix)."""
+        """K X or M X from the band (libbfe2 `bfe2_band_matvec`: thread per entry of the result)."""
+        from . import _lib
         band = self.Mb if mass else self.Kb
         vec = X.dim() == 1
-        X2 = X.reshape(self.n, -1)
-        Y = band[0][:, None] * X2
-        for d in range(1, self.plan.hbw + 1):
-            b = band[d][:self.n - d, None]
-            Y[d:] += b * X2[:self.n - d]
-            Y[:self.n - d] += b * X2[d:]
+        X2 = X.reshape(self.n, -1).contiguous()
+        Y = torch.empty_like(X2) if (out is None or vec or not out.is_contiguous()) else out
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bfe2_band_matvec(self.n, self.plan.hbw, X2.shape[1], _lib.ptr(band), _lib.ptr(X2),
+                                                   _lib.ptr(Y), torch.cuda.current_stream().cuda_stream))
         if vec:
             Y = Y.reshape(self.n)
-        if out is None:
-            return Y
-        out.copy_(Y)
-        return out
+        if out is not None and Y is not out:
+            out.copy_(Y)
+            return out
+        return Y
 
     def modes(self, n_modes=20, tol=1e-11, maxit=80):
         """dict(lam [k] ascending, phi [k, sumdof] M-normalised with zeros at supports, iterations, residual, converged)."""

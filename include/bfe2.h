@@ -251,6 +251,12 @@ int bfe2_internal_actions_ex(bfe2_plan* plan, int64_t B, int32_t C, int32_t npts
 int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const double* Mb, const double* phi,
                              double* gamma, void* stream);
 
+/* ---- Y [n, nrhs] = A X for a symmetric band matrix in the lower-band layout of bfe2_assemble_banded ([hbw+1, n],
+ *      ONE structure) and a row-major multi-vector: the K X / M X products of the first-k modal route of large frames
+ *      (beamfe2_b200/frame_modes.py; the reference forms dense products, Solver.py:39). */
+int bfe2_band_matvec(int32_t n, int32_t hbw, int32_t nrhs, const double* band, const double* X, double* Y,
+                     void* stream);
+
 /* ---- geometric stiffness and linear buckling (HermitianBeam_2D.py:261-282 _Ke_geom,
  *      Structure.py:211-214 K_geom, helpers.py:22-27 geometrical branch, Solver.py:90-180 BucklingSolver -- unfinished
  *      in the reference, README.md:27).  Kgb [B, hbw+1, n]: condensed band of K_g for the axial forces

@@ -150,9 +150,11 @@ def test_lumped_mass_with_condensed_rotations():
     assert lam.shape == (60,) and (lam > 0).all() and (np.diff(lam) >= 0).all()
     # Guyan condensation on the host: K* = Ktt - Ktr Krr^-1 Krt, M* = Mtt (diagonal)
     conn = pm['conn']
-    K, M = orc.assemble_dense(pm['coords'][None], conn, pm['props'][None], lumped=pm['lumped'])
+    Kg, Mg = orc.element_km_global(pm['coords'], conn, pm['props'], pm['lumped'])
+    K = orc.compile_global_matrix(Kg, conn, len(model['nodes']))
+    M = orc.compile_global_matrix(Mg, conn, len(model['nodes']))
     keep = orc.free_positions(len(model['nodes']), pm['fixed'])
-    Kc, Mc = K[0][np.ix_(keep, keep)], M[0][np.ix_(keep, keep)]
+    Kc, Mc = K[np.ix_(keep, keep)], M[np.ix_(keep, keep)]
     t = np.array([p % 3 != 2 for p in keep])
     Ks = Kc[np.ix_(t, t)] - Kc[np.ix_(t, ~t)] @ np.linalg.solve(Kc[np.ix_(~t, ~t)], Kc[np.ix_(~t, t)])
     ref = sla.eigh(Ks, np.diag(np.diag(Mc)[t]), eigvals_only=True)

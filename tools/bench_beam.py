@@ -38,6 +38,9 @@ def main():
     spectrum = bo.cantilever_spectrum(L, E, I, rho, A, args.modes)
     out = {'n_elem': n, 'n_dof': 3 * (n + 1), 'cond_estimate': 16.0 * n ** 4, 'precision': args.precision}
 
+    # warm-up on a small chain: CUDA loads the kernels of the library lazily, on first use
+    wp = sweep.beam_pack(64, length=L, device=dev)
+    LargeBeam(wp['coords'][0], wp['props'][0], [0, 1, 2], precision=args.precision).static(wp['f_nodal'][0, 0])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     beam = LargeBeam(coords, props, [0, 1, 2], n_partitions=args.partitions, precision=args.precision)
