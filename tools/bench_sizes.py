@@ -1,7 +1,14 @@
-import sys, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+"""Fused modal + 10 shapes on chains of growing size: structures/s per n_free, for either modal engine.
+    python tools/bench_sizes.py [jacobi|two_ended]"""
+import os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from beamfe2_b200 import batch
 from beamfe2_b200.plan import Plan
+ENGINE = sys.argv[1] if len(sys.argv) > 1 else 'jacobi'
+batch.set_modal_engine(ENGINE)
+print('# engine', ENGINE)
+
+
 def run(nn, B):
     xy = np.stack([np.arange(nn) * 500.0, np.zeros(nn)], 1)
     conn = np.array([(k, k + 1) for k in range(nn - 1)], dtype=np.int32)
@@ -19,4 +26,6 @@ def run(nn, B):
     ms = e0.elapsed_time(e1) / 3
     print('n_free %3d  B %d  %.2f ms  %.0f structures/s  sweeps %.2f  info %d' % (plan.n_free, B, ms, B / ms * 1e3, out['sweeps'].double().mean().item(), int(out['info'].abs().sum())))
 for nn, B in ((11, 100000), (20, 100000), (21, 50000), (22, 50000), (23, 20000), (25, 20000), (27, 20000), (31, 20000), (34, 10000), (39, 10000)):
+    if ENGINE == 'two_ended' and 3 * (nn - 1) > 64:
+        continue
     run(nn, B)
