@@ -21,6 +21,7 @@ SYMBOLS = (
     'bfe2_beam_solve_dd', 'bfe2_beam_matvec', 'bfe2_beam_residual', 'bfe2_beam_export_blocks',
     'bfe2_gram_workspace_bytes', 'bfe2_gram64', 'bfe2_update64',
     'bfe2_internal_actions', 'bfe2_internal_actions_ex', 'bfe2_modal_participation', 'bfe2_assemble_geometric', 'bfe2_band_matvec',
+    'bfe2_band_matvec_batched', 'bfe2_gram64_batched', 'bfe2_update64_batched',
 )
 
 ARR_CONN, ARR_FREE_OF_POS, ARR_POS_OF_FREE, ARR_FIXED, ARR_SLOT_PTR, ARR_CONTRIB, ARR_NODE_PTR, \
@@ -125,6 +126,12 @@ def lib():
     L.bfe2_internal_actions.argtypes = [vp, i64, i32, i32] + [vp] * 7
     L.bfe2_internal_actions_ex.restype = C.c_int
     L.bfe2_internal_actions_ex.argtypes = [vp, i64, i32, i32] + [vp] * 4 + [i32] + [vp] * 4
+    L.bfe2_band_matvec_batched.restype = C.c_int
+    L.bfe2_band_matvec_batched.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp]
+    L.bfe2_gram64_batched.restype = C.c_int
+    L.bfe2_gram64_batched.argtypes = [i64, i64, vp, vp, vp, vp]
+    L.bfe2_update64_batched.restype = C.c_int
+    L.bfe2_update64_batched.argtypes = [i64, i64, vp, vp, vp, vp]
     L.bfe2_band_matvec.restype = C.c_int
     L.bfe2_band_matvec.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     L.bfe2_assemble_geometric.restype = C.c_int

@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(256) k_gram_partial(long long n, const double*
     double acc[8][2];
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    // blockIdx.y = structure of a batch (bfe2_gram64_batched): every structure has its own [n, 64] pair
+    X += (long long)blockIdx.y * n * GQ;
+    Y += (long long)blockIdx.y * n * GQ;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(n, r0 + rows_per_block);
     for (long long base = r0; base < r1; base += GCH) {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256) k_gram_partial(long long n, const double*
             }
         }
     }
-    double* out = Cpart + (long long)blockIdx.x * GQ * GQ;
+    double* out = Cpart + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * GQ * GQ;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {                                       // C[row gid][cols 2 tig, 2 tig + 1]
         out[(8 * w + gid) * GQ + 8 * t + 2 * tig] = acc[t][0];
@@ -231,6 +234,9 @@ __global__ void __launch_bounds__(256) k_update(long long n, const double* __res
     double* Qs = upd_smem + GQ * GS;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
+    Z += (long long)blockIdx.y * n * GQ;                                // blockIdx.y = structure of a batch
+    Xout += (long long)blockIdx.y * n * GQ;
+    Q += (long long)blockIdx.y * GQ * GQ;
     const long long base = (long long)blockIdx.x * GQ;
     for (int i = tid; i < GQ * GQ; i += 256) {
         const int rr = i / GQ, cc = i % GQ;
@@ -475,6 +481,25 @@ int bfe2_update64(int64_t n, const double* Z, const double* Q, double* Xout, voi
     const size_t smem = 2 * GQ * GS * sizeof(double);
     BEAM_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_update<<<(unsigned)((n + GQ - 1) / GQ), 256, smem, (cudaStream_t)stream>>>(n, Z, Q, Xout);
+    BEAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// batched forms for the first-k modal route of MANY mid-size frames (beamfe2_b200/frame_modes.BatchedFrameModes):
+// X, Y, Z, Xout [B, n, 64], C, Q [B, 64, 64]; one block per structure walks all rows (n is a few hundred to a few thousand)
+int bfe2_gram64_batched(int64_t n, int64_t B, const double* X, const double* Y, double* C, void* stream) {
+    if (n < 1 || B < 1 || B > 65535 || !X || !Y || !C) return bfe2_fail(-1, "bfe2_gram64_batched: bad argument");
+    const long long rpb = (n + GCH - 1) / GCH * GCH;
+    k_gram_partial<<<dim3(1, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(n, X, Y, C, rpb);
+    BEAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bfe2_update64_batched(int64_t n, int64_t B, const double* Z, const double* Q, double* Xout, void* stream) {
+    if (n < 1 || B < 1 || B > 65535 || !Z || !Q || !Xout || Z == Xout) return bfe2_fail(-1, "bfe2_update64_batched: bad argument");
+    const size_t smem = 2 * GQ * GS * sizeof(double);
+    BEAM_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_update<<<dim3((unsigned)((n + GQ - 1) / GQ), (unsigned)B), 256, smem, (cudaStream_t)stream>>>(n, Z, Q, Xout);
     BEAM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -180,6 +180,10 @@ __global__ void k_assemble_geometric(PlanDev P, long long B, const double* __res
 // thread per (row, column); used by the first-k modal route of large frames (K X, M X of the subspace iteration)
 __global__ void k_band_matvec(int n, int hbw, int nrhs, const double* __restrict__ band, const double* __restrict__ X,
                               double* __restrict__ Y) {
+    // blockIdx.y = structure of a batch: its own band [hbw+1, n] and vectors [n, nrhs]
+    band += (long long)blockIdx.y * (hbw + 1) * n;
+    X += (long long)blockIdx.y * n * nrhs;
+    Y += (long long)blockIdx.y * n * nrhs;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * nrhs) return;
     const int i = (int)(t / nrhs), r = (int)(t % nrhs);
@@ -194,6 +198,16 @@ __global__ void k_band_matvec(int n, int hbw, int nrhs, const double* __restrict
 }  // namespace
 
 extern "C" {
+
+int bfe2_band_matvec_batched(int32_t n, int32_t hbw, int32_t nrhs, int64_t B, const double* band, const double* X,
+                             double* Y, void* stream) {
+    if (n < 1 || hbw < 0 || nrhs < 1 || B < 1 || B > 65535 || !band || !X || !Y || X == Y)
+        return bfe2_fail(-1, "bfe2_band_matvec: bad argument");
+    const long long total = (long long)n * nrhs;
+    k_band_matvec<<<dim3((unsigned)((total + 127) / 128), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(n, hbw, nrhs, band, X, Y);
+    if (cudaGetLastError() != cudaSuccess) return bfe2_fail(-100, "k_band_matvec launch failed");
+    return 0;
+}
 
 int bfe2_band_matvec(int32_t n, int32_t hbw, int32_t nrhs, const double* band, const double* X, double* Y, void* stream) {
     if (n < 1 || hbw < 0 || nrhs < 1 || !band || !X || !Y || X == Y) return bfe2_fail(-1, "bfe2_band_matvec: bad argument");

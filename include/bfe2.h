@@ -256,6 +256,13 @@ int bfe2_modal_participation(bfe2_plan* plan, int64_t B, int32_t n_modes, const 
  *      (beamfe2_b200/frame_modes.py; the reference forms dense products, Solver.py:39). */
 int bfe2_band_matvec(int32_t n, int32_t hbw, int32_t nrhs, const double* band, const double* X, double* Y,
                      void* stream);
+/*      ... and the batched forms of the three block products (band [B, hbw+1, n]; X, Y, Z, Xout [B, n, nrhs = 64];
+ *      C, Q [B, 64, 64]; B <= 65535) for the first-k modes of MANY frames at once
+ *      (beamfe2_b200/frame_modes.BatchedFrameModes: 116 < n_free). */
+int bfe2_band_matvec_batched(int32_t n, int32_t hbw, int32_t nrhs, int64_t B, const double* band, const double* X,
+                             double* Y, void* stream);
+int bfe2_gram64_batched(int64_t n, int64_t B, const double* X, const double* Y, double* C, void* stream);
+int bfe2_update64_batched(int64_t n, int64_t B, const double* Z, const double* Q, double* Xout, void* stream);
 
 /* ---- geometric stiffness and linear buckling (HermitianBeam_2D.py:261-282 _Ke_geom,
  *      Structure.py:211-214 K_geom, helpers.py:22-27 geometrical branch, Solver.py:90-180 BucklingSolver -- unfinished

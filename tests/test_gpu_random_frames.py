@@ -186,6 +186,68 @@ def test_first_modes_of_a_frame_beyond_the_jacobi_path():
     assert np.abs(om / np.sqrt(w[:20]) - 1).max() < 1e-8
 
 
+def test_first_modes_of_many_frames_in_one_batch():
+    """BatchedFrameModes: 24 variants (sections, moduli, masses, node jitter) of a 3-storey, 4-bay frame with
+    n_free = 150 > 116 in ONE sequence of launches; every variant's 12 lowest eigenpairs against scipy.linalg.eigh on
+    the oracle's dense matrices, and against the single-structure FrameModes."""
+    import scipy.linalg as sla
+    from beamfe2_b200.frame_modes import BatchedFrameModes, FrameModes
+    storeys, bays, H, Lb = 3, 4, 3000.0, 5000.0
+    nodes, idx = [], {}
+
+    def node(x, y):
+        key = (round(x, 6), round(y, 6))
+        if key not in idx:
+            idx[key] = len(nodes)
+            nodes.append((x, y))
+        return idx[key]
+    conn, kinds = [], []
+    for b in range(bays + 1):
+        for s_ in range(storeys):
+            ys = [s_ * H, s_ * H + H / 2, (s_ + 1) * H]
+            for a, c in zip(ys[:-1], ys[1:]):
+                conn.append((node(b * Lb, a), node(b * Lb, c)))
+                kinds.append(0)
+    for s_ in range(1, storeys + 1):
+        for b in range(bays):
+            xs = [b * Lb, b * Lb + Lb / 2, (b + 1) * Lb]
+            for a, c in zip(xs[:-1], xs[1:]):
+                conn.append((node(a, s_ * H), node(c, s_ * H)))
+                kinds.append(1)
+    xy = np.array(nodes)
+    conn = np.array(conn, dtype=np.int32)
+    kinds = np.array(kinds)
+    fixed = sorted(3 * i + d for i, (x, y) in enumerate(nodes) if y == 0.0 for d in range(3))
+    plan = Plan(len(nodes), conn, fixed, reorder=True)
+    assert plan.n_free > 116
+    B = 24
+    rng = np.random.default_rng(5)
+    coords = xy[None] + rng.uniform(-50, 50, (B,) + xy.shape) * (xy[None, :, 1:2] > 0)      # supports stay put
+    base = np.where(kinds[:, None] == 0, [[2.1e5, 300.0 * 300.0, 300.0 ** 4 / 12, 7.85e-9]],
+                    [[2.1e5, 200.0 * 500.0, 200.0 * 500.0 ** 3 / 12, 7.85e-9]])
+    props = base[None] * rng.uniform(0.7, 1.4, (B, len(conn), 1))
+    mass = np.zeros((B, len(nodes), 2))
+    floor = [i for i, (x, y) in enumerate(nodes) if y > 0 and abs(y / H - round(y / H)) < 1e-9]
+    mass[:, floor, :] = rng.uniform(0.5, 4.0, (B, 1, 1))
+
+    def T(a):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+    bf = BatchedFrameModes(plan, T(coords), T(props), T(mass))
+    out = bf.modes(n_modes=12)
+    assert bool(out['converged'].all()) and out['iterations'] < 40
+    assert float(out['residual'].max().item()) < 1e-9
+    lam = out['lam'].cpu().numpy()
+    keep = np.setdiff1d(np.arange(plan.sumdof), fixed)
+    for b in range(0, B, 5):
+        o = orc.solve_batch(conn, fixed, coords[b], props[b], nodal_mass=mass[b])
+        w = sla.eigh(o['Kc'], o['Mc'], eigvals_only=True)
+        assert np.abs(lam[b] / w[:12] - 1).max() < 1e-8, b
+        phi = out['phi'][b].cpu().numpy()[:, keep]
+        assert np.abs(phi @ o['Mc'] @ phi.T - np.eye(12)).max() < 1e-8
+    one = FrameModes(plan, T(coords[3]), T(props[3]), T(mass[3])).modes(n_modes=12)
+    assert np.abs(lam[3] / one['lam'].cpu().numpy() - 1).max() < 1e-9
+
+
 @pytest.mark.parametrize('n_nodes,extra,C,B,reorder', [
     (4, 0, 1, 1, False), (6, 1, 3, 3, True), (9, 2, 5, 45, True), (12, 3, 17, 7, True),
     (16, 4, 2, 1000, True), (20, 0, 3, 33, True), (25, 6, 4, 5, False), (30, 3, 3, 129, True)])
