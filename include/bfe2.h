@@ -193,7 +193,8 @@ int bfe2_sym_eig_dense(bfe2_plan* dense_plan, int64_t Bt, const double* A, const
  *      Multi-vectors are [n_dof, nrhs] row-major (the nrhs values of a DOF are contiguous).
  *      Precision: cond(K) ~ 16 n^4 (1.6e21 at n = 1e5), so the element matrices, the factorisation and the
  *      substitutions run in double-double (BFE2_BEAM_DD, the default of bfe2_beam_create; the inputs are exact
- *      FP64 numbers, eps * cond stays ~2e-11); BFE2_BEAM_FP64 instantiates the same kernels in plain FP64. ---- */
+ *      FP64 numbers, eps * cond stays ~2e-11); BFE2_BEAM_FP64 instantiates the same kernels in plain FP64.
+ *      A handle owns scratch for the low words of a running solve: use it from ONE stream at a time. ---- */
 typedef struct bfe2_beam bfe2_beam;
 #define BFE2_BEAM_FP64 0
 #define BFE2_BEAM_DD   1
