@@ -804,10 +804,12 @@ int dispatch_static_group(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A
 // ---- K3 / K4 / fused: one block per structure ----------------------------------------------------
 //   ASSEMBLE = 1: inputs are coords/props(/mass) and the bands are assembled in shared memory;
 //   ASSEMBLE = 0: bands are read from HBM (unfused K3 / K4).
+//   REGS = 1: register-resident Jacobi (n <= 64); 2: the two-column-group register variant (64 < n <= 116, fused
+//   path); 0: columns exchanged through shared memory (stage_jacobi_oe).
 //   PACKED = 1: packed records / compact layouts (bfe2_solve_fused_packed); a separate instantiation, so that the
 //   dense kernel carries none of that code (the register-resident sweep loop is sensitive to what ptxas has to
 //   keep around it: with run-time flags the dense P20 launch went from 46.0 to 49.9 ms).
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS, bool PACKED = false>
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, int REGS, bool PACKED = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_solve(PlanDev P, BatchArgs A) {
     extern __shared__ __align__(16) double smem[];
@@ -956,8 +958,10 @@ k_solve(PlanDev P, BatchArgs A) {
             if (s_flag[1] == 0) {
                 double* s_W = smem + L.U;
                 stage_form_a(P, smem + L.Kb, smem + L.Mb, smem + L.invM, s_W, tid, nt, early_k ? &kcol : nullptr, ASSEMBLE);
-                if constexpr (REGS) {
+                if constexpr (REGS == 1) {
                     sw = stage_jacobi_regs<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
+                } else if constexpr (REGS == 2) {   // 64 < n <= 116: two column groups x LPP row chunks, NT = 64 LPP
+                    sw = stage_jacobi_regs2<RPL, LPP, true>(P, s_W, A.max_sweeps, tid);
                 } else {
                     sw = pivoted_cholesky_smem(P, s_W, smem + L.lam, s_order, tid, nt)
                              ? stage_jacobi_oe<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid) : INT_MIN;
@@ -995,7 +999,7 @@ k_solve(PlanDev P, BatchArgs A) {
     if (tid == 0) *outs().info = info;
 }
 
-template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, bool REGS, bool PACKED = false>
+template <int RPL, int LPP, int NT, int MINB, bool ASSEMBLE, int REGS, bool PACKED = false>
 int launch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaStream_t stream) {
     const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, plan->npad, plan->LD, A.C);
     PlanDev P = pd;
@@ -1093,17 +1097,25 @@ int dispatch_solve(bfe2_plan* plan, const PlanDev& pd, const BatchArgs& A, cudaS
     // n <= 64: register-resident, preconditioned odd-even Jacobi (two warps per structure);
     // 64 < n <= 116: shared-memory round-robin variant (four lanes per column pair).
     if (plan->lpp == 2) {
-        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
-        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 5) return launch_solve<5, 2, 64, 8, ASSEMBLE, 1, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 15) return launch_solve<15, 2, 64, 8, ASSEMBLE, 1, PACKED>(plan, pd, A, stream);
         // __launch_bounds__(64, 5): same 168 registers and 6 resident blocks as (64, 6), but ptxas schedules the
         // software-pipelined step better (+4.7 % measured); (64, 4) takes 216 registers, 4 blocks and is slower.
-        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
-        if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, true, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 29) return launch_solve<29, 2, 64, 5, ASSEMBLE, 1, PACKED>(plan, pd, A, stream);
+        if (plan->rpl == 32) return launch_solve<32, 2, 64, 5, ASSEMBLE, 1, PACKED>(plan, pd, A, stream);
     }
-    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 3, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
-    if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
-    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 2, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
-    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, false, PACKED>(plan, pd, A, stream);
+    if constexpr (ASSEMBLE) {
+        // fused path, 100 < n <= 116: registers, two column groups x four row chunks (256 threads): +20 % over the
+        // shared-memory exchange variant there; below, with fewer rows per lane, the exchange variant's three resident
+        // blocks win (profiles/r2_sizes.txt).  BFE2_MIDSIZE_SMEM=1 forces the exchange variant for comparison.
+        static const bool smem_variant = getenv("BFE2_MIDSIZE_SMEM") != nullptr;
+        if (!smem_variant && plan->lpp == 4 && plan->rpl == 29)
+            return launch_solve<29, 4, 256, 1, ASSEMBLE, 2, PACKED>(plan, pd, A, stream);
+    }
+    if (plan->rpl == 18 && plan->lpp == 4) return launch_solve<18, 4, 160, 3, ASSEMBLE, 0, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 22 && plan->lpp == 4) return launch_solve<22, 4, 192, 2, ASSEMBLE, 0, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 25 && plan->lpp == 4) return launch_solve<25, 4, 224, 2, ASSEMBLE, 0, PACKED>(plan, pd, A, stream);
+    if (plan->rpl == 29 && plan->lpp == 4) return launch_solve<29, 4, 256, 1, ASSEMBLE, 0, PACKED>(plan, pd, A, stream);
     return fail(-3, "n_free = %d is beyond the shared-memory Jacobi path (max %d)", plan->n, BFE2_MAX_JACOBI_N);
 }
 
@@ -1578,7 +1590,7 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, C);
         const size_t bytes = (size_t)L.total * sizeof(double);
         if (bytes > 227 * 1024) return launch_static_global<true>(plan, pd, A, (cudaStream_t)stream);
-        auto kern = k_solve<5, 2, 64, 8, true, false>;
+        auto kern = k_solve<5, 2, 64, 8, true, 0>;
         BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
         kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);
@@ -1721,7 +1733,7 @@ int bfe2_solve_fused_packed(bfe2_plan* plan, bfe2_pattern* q, int64_t B, const d
         const SmemLayout L = make_layout(plan->nN, plan->nE, plan->n, plan->hbw, 0, 0, q->C);
         const size_t bytes = (size_t)L.total * sizeof(double);
         if (bytes > 227 * 1024) return fail(-3, "structure needs %zu bytes of shared memory (> 227 KB)", bytes);
-        auto kern = k_solve<5, 2, 64, 8, true, false, true>;
+        auto kern = k_solve<5, 2, 64, 8, true, 0, true>;
         BFE2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (B > 0x7fffffffLL) return fail(-2, "batch too large for one launch");
         kern<<<(unsigned)B, 64, bytes, (cudaStream_t)stream>>>(P, A);

@@ -1038,6 +1038,261 @@ __device__ __forceinline__ bool pivoted_cholesky_smem(const PlanDev& P, double* 
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident Jacobi for 64 < n <= 128 (round 2): the same odd-even ordering with TWO column groups.
+//   Warp (cg, h): column group cg (pairs 32 cg .. 32 cg + 31, one pair per lane), row chunk h (rows h RPL ..).
+//   Inside a group the moving column travels by warp shuffle exactly as in the one-group variant; the two pairs per
+//   step whose neighbour lives in the OTHER group (pair 31 <-> 32 and the cyclic wrap NP-1 <-> 0) hand their column
+//   over through a slot in shared memory: the exporting lane stores it while it rotates, after ONE extra block barrier
+//   the importing lane loads it and redoes its part of the next dot product.  Two barriers per step instead of one,
+//   but no column ever makes the round trip through shared memory that the 4-lanes-per-pair variant
+//   (stage_jacobi_oe) pays on every pair and step.
+// ------------------------------------------------------------------------------------------------
+template <int RPL, bool ODD>
+__device__ __forceinline__ void jacobi_regs2_step(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
+                                                  int& unsettled, double g, unsigned pg_mine, bool act, bool last, int src,
+                                                  bool exp, unsigned exp_addr) {
+    const double gg = g * g, pab = nA * nB;
+    const bool live = act && !(ODD && last);
+    const bool rot = live && (gg > (BFE2_JACOBI_TOL * BFE2_JACOBI_TOL) * pab);
+    if (live && gg > (BFE2_JACOBI_TAU_WIDE * BFE2_JACOBI_TAU_WIDE) * pab) unsettled = 1;
+    double c = 1.0, s = 0.0;
+    if (ODD && last && act) {                         // exchange the two idle end columns
+        c = 0.0; s = -1.0;
+        const double tmp = nA; nA = nB; nB = tmp;
+    }
+    if (rot) {
+        const double d = nB - nA, hh = 2.0 * g;
+        const double ir = rsqrt_fast(fma(d, d, hh * hh));
+        const double hs = (d < 0.0) ? -hh : hh;
+        const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+        const double ic = rsqrt_fast(c2);
+        c = c2 * ic;
+        s = (0.5 * hs * ir) * ic;
+        const double tg = (s * ic) * g;
+        nA -= tg;
+        nB += tg;
+        if (fabs(s) > BFE2_JACOBI_TAU_WIDE) unsettled = 1;
+    }
+    if (exp) sts_f64(exp_addr + 8u * RPL, ODD ? nA : nB);   // norm of the column that leaves
+    double acc0 = 0.0, acc1 = 0.0;
+    if (__any_sync(0xffffffffu, rot || (ODD && last && act))) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const double sb = s * B[r], cb = c * B[r];
+            const double nb = fma(s, A[r], cb);
+            const double na = fma(c, A[r], -sb);
+            if (exp) sts_f64(exp_addr + 8u * r, ODD ? na : nb);
+            if (!ODD) { A[r] = na; B[r] = __shfl_sync(0xffffffffu, nb, src); }
+            else { B[r] = nb; A[r] = __shfl_sync(0xffffffffu, na, src); }
+            if (r & 1) acc1 = fma(A[r], B[r], acc1); else acc0 = fma(A[r], B[r], acc0);
+        }
+    } else {                                          // nobody in this warp rotates: move and multiply only
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            if (exp) sts_f64(exp_addr + 8u * r, ODD ? A[r] : B[r]);
+            if (!ODD) B[r] = __shfl_sync(0xffffffffu, B[r], src);
+            else A[r] = __shfl_sync(0xffffffffu, A[r], src);
+            if (r & 1) acc1 = fma(A[r], B[r], acc1); else acc0 = fma(A[r], B[r], acc0);
+        }
+    }
+    if (!ODD) nB = __shfl_sync(0xffffffffu, nB, src);
+    else nA = __shfl_sync(0xffffffffu, nA, src);
+    sts_f64(pg_mine, acc0 + acc1);
+}
+
+// named barrier of the two warps (group 0 and group 1) that own row chunk h: 64 threads, barrier resource 1 + h
+__device__ __forceinline__ void pair_barrier(int h) {
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + h) : "memory");
+}
+
+// the column (and its norm) that arrives from the other column group: reload it and redo this lane's partial dot product
+template <int RPL, bool ODD>
+__device__ __forceinline__ void jacobi_regs2_import(double (&A)[RPL], double (&B)[RPL], double& nA, double& nB,
+                                                    unsigned in_addr, unsigned pg_mine) {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const double v = lds_f64(in_addr + 8u * r);
+        if (!ODD) B[r] = v; else A[r] = v;
+        if (r & 1) acc1 = fma(A[r], B[r], acc1); else acc0 = fma(A[r], B[r], acc0);
+    }
+    if (!ODD) nB = lds_f64(in_addr + 8u * RPL); else nA = lds_f64(in_addr + 8u * RPL);
+    sts_f64(pg_mine, acc0 + acc1);
+}
+
+// pivoted Cholesky in the two-group register layout (see pivoted_cholesky_regs): each group proposes its largest
+// remaining diagonal entry, one extra barrier per step makes the choice global
+template <int RPL, int NW>
+__device__ __forceinline__ bool pivoted_cholesky_regs2(double (&A)[RPL], double (&B)[RPL], double dA, double dB,
+                                                       int n, double* lbuf, int lane, int h, int cg, bool act) {
+    constexpr int RPLP = (RPL + 2) & ~1;
+    const double NEG = -INFINITY;
+    const int cA = 2 * (32 * cg + lane), cB = cA + 1;
+    const int iA = (cA / RPL) * RPLP + cA % RPL, iB = (cB / RPL) * RPLP + cB % RPL;
+    int* step_of = reinterpret_cast<int*>(lbuf + 2 * NW * RPLP);          // [NW * RPL] ints
+    double* cand = lbuf + 2 * NW * RPLP + (NW * RPL + 2) / 2;             // [2 parity][2 groups][dp, column]
+    double rsA = 0.0, rsB = 0.0;
+    int kA = 0, kB = 0;
+    for (int k = 0; k < n; ++k) {
+        const double dm = fmax(dA, dB);
+        const unsigned key = dm > 0.0 ? (unsigned)__double2hiint(dm) : 0u;
+        const unsigned best = __reduce_max_sync(0xffffffffu, key);
+        const int src = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+        const int p_loc = __shfl_sync(0xffffffffu, dA >= dB ? cA : cB, src);
+        const double dp_loc = __shfl_sync(0xffffffffu, dm, src);
+        double* cd = cand + (k & 1) * 4;
+        if (h == 0 && lane == 0) { cd[2 * cg] = dp_loc; cd[2 * cg + 1] = (double)p_loc; }
+        __syncthreads();
+        const double d0 = cd[0], d1 = cd[2];
+        const bool second = d1 > d0;                   // ties and NaNs go to group 0: the same choice in every warp
+        const int p = (int)(second ? cd[3] : cd[1]);
+        const double dp = second ? d1 : d0;
+        if (!(dp > 0.0) || !isfinite(dp)) return false;          // uniform over the block
+        const double ip = rcp_fast(dp);
+        double* lb = lbuf + (k & 1) * (NW * RPLP);
+        if (cg == (p >> 6) && lane == ((p >> 1) & 31)) {
+            double* dst = lb + h * RPLP;
+            if (p & 1) {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) dst[r] = B[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) dst[r] = A[r];
+            }
+            if (h == 0) step_of[p] = k;
+        }
+        __syncthreads();
+        double mA = (act && dA != NEG) ? lb[iA] : 0.0, mB = (act && dB != NEG) ? lb[iB] : 0.0;
+        if (cA == p) { mA = 0.0; dA = NEG; kA = k; rsA = rsqrt_fast(dp); }
+        if (cB == p) { mB = 0.0; dB = NEG; kB = k; rsB = rsqrt_fast(dp); }
+        dA = fma(-mA * ip, mA, dA);
+        dB = fma(-mB * ip, mB, dB);
+        mA *= ip;
+        mB *= ip;
+        const double2* l2 = reinterpret_cast<const double2*>(lb + h * RPLP);
+#pragma unroll
+        for (int r = 0; r < RPL; r += 2) {
+            const double2 l = l2[r >> 1];
+            A[r] = fma(-l.x, mA, A[r]);
+            B[r] = fma(-l.x, mB, B[r]);
+            if (r + 1 < RPL) {
+                A[r + 1] = fma(-l.y, mA, A[r + 1]);
+                B[r + 1] = fma(-l.y, mB, B[r + 1]);
+            }
+        }
+    }
+    __syncthreads();
+    const int row0 = h * RPL;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int tr = (row0 + r < n) ? step_of[row0 + r] : -1;
+        A[r] = (tr < kA) ? 0.0 : A[r] * rsA;
+        B[r] = (tr < kB) ? 0.0 : B[r] * rsB;
+    }
+    __syncthreads();
+    return true;
+}
+
+template <int RPL, int NW, bool PRECOND = false>
+__device__ __forceinline__ int stage_jacobi_regs2(const PlanDev& P, double* s_W, int max_sweeps, int tid) {
+    const int lane = tid & 31, wid = tid >> 5;
+    const int cg = wid / NW, h = wid - cg * NW;        // column group, row chunk
+    const int npad = P.npad, LD = P.LD, NP = npad >> 1;
+    const int pr = 32 * cg + lane;                    // pair (line positions 2 pr, 2 pr + 1)
+    const bool act = pr < NP;
+    const bool last = pr == NP - 1;
+    const int lastlane = cg == 0 ? 31 : NP - 33;      // last active lane of this group (NP > 32 here)
+    const int src_dn = (act && lane < lastlane) ? lane + 1 : lane;     // the group's last lane imports instead
+    const int src_up = (act && lane > 0) ? lane - 1 : lane;            // lane 0 imports instead
+    double A[RPL], B[RPL];
+    {
+        const double* pa = s_W + (2 * pr) * LD + h * RPL;
+        const double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            A[r] = act ? pa[r] : 0.0;
+            B[r] = act ? pb[r] : 0.0;
+        }
+    }
+    double dA = -INFINITY, dB = -INFINITY;
+    if (PRECOND && act) {
+        if (2 * pr < P.n) dA = s_W[(2 * pr) * LD + 2 * pr];
+        if (2 * pr + 1 < P.n) dB = s_W[(2 * pr + 1) * LD + 2 * pr + 1];
+    }
+    __syncthreads();                                  // W is in registers: its memory becomes scratch
+    constexpr int W32 = 2 * NW * 32;                  // lanes of the block
+    constexpr int SLOT = RPL + 2;                     // exported column + its norm
+    constexpr int OFF_EXP = 5 * W32, OFF_LBUF = (OFF_EXP + 2 * NW * SLOT + 1) & ~1;
+    if (PRECOND) {
+        if (!pivoted_cholesky_regs2<RPL, NW>(A, B, dA, dB, P.n, s_W + OFF_LBUF, lane, h, cg, act)) return INT_MIN;
+    }
+    const unsigned base = (unsigned)__cvta_generic_to_shared(s_W);
+    const unsigned pg0 = base, pg1 = base + W32 * 8u;                  // [2 parity][group][row chunk][lane]
+    const unsigned mine = 8u * ((cg * NW + h) * 32 + lane), w0 = 8u * (cg * NW * 32 + lane);
+    double* part_n = s_W + 2 * W32;                                    // [W32][3]
+    const unsigned slot_mine = base + 8u * (OFF_EXP + (cg * NW + h) * SLOT);
+    const unsigned slot_other = base + 8u * (OFF_EXP + ((1 - cg) * NW + h) * SLOT);
+    // even steps: B comes from pair + 1 -- lane 0 of each group exports, the group's last active lane imports;
+    // odd steps:  A comes from pair - 1 -- the group's last active lane exports, lane 0 imports
+    const bool exp_even = act && lane == 0, imp_even = act && lane == lastlane;
+    const bool exp_odd = act && lane == lastlane, imp_odd = act && lane == 0;
+    int sweeps = 0;
+    bool converged = false;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        double nA = 0.0, nB = 0.0, g = 0.0;
+        {
+            double a0 = 0.0, b0 = 0.0, c0 = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                a0 = fma(A[r], A[r], a0);
+                b0 = fma(B[r], B[r], b0);
+                c0 = fma(A[r], B[r], c0);
+            }
+            const int me = ((cg * NW + h) * 32 + lane) * 3;
+            part_n[me] = a0;
+            part_n[me + 1] = b0;
+            part_n[me + 2] = c0;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {            // same order in every warp of the group: identical bits
+                const int o = ((cg * NW + w) * 32 + lane) * 3;
+                nA += part_n[o];
+                nB += part_n[o + 1];
+                g += part_n[o + 2];
+            }
+        }
+        int unsettled = 0;
+#pragma unroll 1
+        for (int step = 0; step < npad; step += 2) {
+            jacobi_regs2_step<RPL, false>(A, B, nA, nB, unsettled, g, pg1 + mine, act, last, src_dn, exp_even, slot_mine);
+            pair_barrier(h);                          // only the two warps of row chunk h exchange a column
+            if (imp_even) jacobi_regs2_import<RPL, false>(A, B, nA, nB, slot_other, pg1 + mine);
+            __syncthreads();
+            g = lds_f64(pg1 + w0);
+#pragma unroll
+            for (int w = 1; w < NW; ++w) g += lds_f64(pg1 + w0 + 256u * w);
+            jacobi_regs2_step<RPL, true>(A, B, nA, nB, unsettled, g, pg0 + mine, act, last, src_up, exp_odd, slot_mine);
+            pair_barrier(h);
+            if (imp_odd) jacobi_regs2_import<RPL, true>(A, B, nA, nB, slot_other, pg0 + mine);
+            __syncthreads();
+            g = lds_f64(pg0 + w0);
+#pragma unroll
+            for (int w = 1; w < NW; ++w) g += lds_f64(pg0 + w0 + 256u * w);
+        }
+        if (!__syncthreads_or(unsettled)) { ++sweeps; converged = true; break; }
+    }
+    __syncthreads();                                  // scratch no longer read: W comes back
+    if (act) {
+        double* pa = s_W + (2 * pr) * LD + h * RPL;
+        double* pb = pa + LD;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) { pa[r] = A[r]; pb[r] = B[r]; }
+    }
+    __syncthreads();
+    return converged ? sweeps : -sweeps;
+}
+
 // PRECOND: s_W holds the symmetric matrix C itself (slot j = column j); it is first replaced, in registers, by its
 // pivoted Cholesky factor Z (C = Z Z^T), and the sweeps orthogonalise the columns of Z:  Z V = U Sigma, so that
 // at convergence column k is  sqrt(lam_k) u_k  with  C u_k = lam_k u_k.  Returns INT_MIN if C is not positive
