@@ -140,3 +140,41 @@ def test_sweep_generator_is_deterministic():
         pm = util.pack(sweep.p20_model_dict(a[k]))
         for key in ('coords', 'props', 'nodal_mass', 'f_nodal', 'r_local'):
             assert np.array_equal(pm[key], pk[key][k].numpy()), key
+
+
+def test_pattern_layout_and_argument_checks():
+    """bfe2_pattern_* (packed records) is host-side bookkeeping: widths / offsets of the records and the argument
+    checks can be pinned without a GPU; the packed solve itself fails loudly without one."""
+    import ctypes as C
+    import torch
+    from beamfe2_b200 import batch
+    L = _lib.lib()
+    conn, sup = sweep.p20_topology()
+    p = Plan.from_supports(21, conn, sup)
+    io = batch.PackedIO(p, 3, 10, True, f_index=[21, 147, 167], r_index=list(range(0, 48)))
+    assert (io.w_in, io.w_out) == (42 + 80 + 42 + 3 + 48, 3 * 57 + 360 + 18 + 57 + 570 + 1)
+    assert io.in_off == [0, 42, 122, 164, 167] and io.out_off == [0, 171, 531, 549, 606, 1176]
+    assert io.n_fixed == 6 and io.out_shapes['reactions'] == (3, 6)
+    dense = batch.PackedIO(p, 3, 10)                      # no pattern given: every load entry travels
+    assert dense.w_in == 42 + 80 + 42 + 189 + 360
+    static_only = batch.PackedIO(p, 2, 0, modal=False, f_index=[0], r_index=[])
+    assert static_only.w_out == 2 * 57 + 240 + 12 + 1
+    # views: strided windows of the record, info / sweeps share one float64 slot
+    rec = torch.zeros((5, io.w_out), dtype=torch.float64)
+    v = io.out_views(rec)
+    v['info'][:] = torch.arange(5, dtype=torch.int32)
+    v['sweeps'][:] = 7
+    v['lam'][:, 0] = 3.5
+    assert rec[2, io.out_off[3]] == 3.5 and v['u'].shape == (5, 3, 57) and v['phi'].shape == (5, 10, 57)
+    assert rec.view(torch.int32)[4, 2 * io.out_off[5]] == 4 and rec.view(torch.int32)[4, 2 * io.out_off[5] + 1] == 7
+    # argument checks
+    h = C.c_void_p()
+    bad = np.array([3 * 63], dtype=np.int32)             # one past the last (lc, position)
+    assert L.bfe2_pattern_create(C.byref(h), p.handle, 3, 1, 10, 1, _lib.ptr(bad), 0, None) == -1
+    assert b'f_index' in L.bfe2_last_error()
+    assert L.bfe2_pattern_create(C.byref(h), p.handle, 0, 0, 0, 0, None, 0, None) == -1          # nothing to do
+    assert L.bfe2_pattern_create(C.byref(h), p.handle, 3, 1, 58, 0, None, 0, None) == -1         # more shapes than DOFs
+    assert L.bfe2_set_modal_engine(7) == -1 and L.bfe2_get_modal_engine() == 0
+    if not torch.cuda.is_available():
+        z = np.zeros(io.w_in + io.w_out)
+        assert L.bfe2_solve_fused_packed(p.handle, io._h, 1, _lib.ptr(z), _lib.ptr(z), None) == -100
