@@ -1,5 +1,6 @@
 import sys, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from beamfe2_b200 import batch
 from beamfe2_b200.plan import Plan
 from oracle import beamfe2_oracle as orc
