@@ -966,15 +966,17 @@ k_solve(PlanDev P, BatchArgs A) {
                     sw = pivoted_cholesky_smem(P, s_W, smem + L.lam, s_order, tid, nt)
                              ? stage_jacobi_oe<RPL, LPP>(P, s_W, smem + L.lam, A.max_sweeps, tid) : INT_MIN;
                 }
-                if (sw != INT_MIN) {
-                    const Outs o = outs();
-                    stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, s_W, smem + L.lam, s_order, A.n_modes,
-                                            o.lam, o.phi, tid, nt, ASSEMBLE, compact_out);
-                }
-                __syncthreads();
             }
         }
+        // K = Lk Lk^T now (unless it was factored up front): the static part needs it, and the modal output stage
+        // refines every eigenvalue as a Rayleigh quotient on the two factors
         if (!early_k) factor(true, false);
+        if (A.do_modal && s_flag[1] == 0 && sw != INT_MIN) {
+            const Outs o = outs();
+            stage_modal_output<LPP>(P, smem + L.Mb, smem + L.invM, smem + L.U, smem + L.lam, s_order, A.n_modes,
+                                    o.lam, o.phi, tid, nt, ASSEMBLE, compact_out, s_flag[0] == 0 ? smem + L.Kb : nullptr);
+            __syncthreads();
+        }
         const int infoK = s_flag[0], infoM = s_flag[1];
         if (infoK != 0) {
             fail_all(infoK);

@@ -1443,21 +1443,121 @@ __device__ __forceinline__ void stage_form_a(const PlanDev& P, const double* s_K
     __syncthreads();
 }
 
+// One pass over a column for the refinement below: phi = Lm^-T (scale * w) by back substitution with the active window
+// in registers and, in the same sweep over the rows, y_j = (Lk^T phi)_j = sum_d Lk[j+d][j] phi[j+d] from the same
+// window.  Returns |Lk^T phi|^2; `flip` tells whether the largest-magnitude entry of phi is negative.  All loads of a
+// row are independent of the recurrence, and the row loop is unrolled so that they are issued in batches.
+template <int HB>
+__device__ __forceinline__ double backsolve_rq(const double* __restrict__ Mf, const double* __restrict__ invM,
+                                               const double* __restrict__ Lk, double* x, int n, int b, double scale,
+                                               bool& flip) {
+    double win[HB];                                  // win[d-1] = phi[j+d]
+#pragma unroll
+    for (int d = 0; d < HB; ++d) win[d] = 0.0;
+    double l0 = 0.0, l1 = 0.0, best = 0.0;
+    flip = false;
+#pragma unroll 4
+    for (int j = n - 1; j >= 0; --j) {
+        double far = x[j] * scale;
+        double y = 0.0;
+#pragma unroll
+        for (int d = HB; d >= 1; --d) {
+            const bool in = d <= b && j + d < n;
+            const double lm = in ? Mf[d * n + j] : 0.0;
+            const double lk = in ? Lk[d * n + j] : 0.0;
+            far = fma(-lm, win[d - 1], far);
+            y = fma(lk, win[d - 1], y);
+        }
+        const double v = far * invM[j];
+        y = fma(Lk[j], v, y);
+        if (j & 1) l1 = fma(y, y, l1); else l0 = fma(y, y, l0);
+#pragma unroll
+        for (int d = HB - 1; d >= 1; --d) win[d] = win[d - 1];
+        win[0] = v;
+        x[j] = v;
+        const double av = fabs(v);
+        if (av >= best) { best = av; flip = v < 0.0; }   // rows descend: on a tie the LOWER index decides, as before
+    }
+    return l0 + l1;
+}
+
+// Rayleigh-quotient refinement of every column (see stage_modal_output).  Kept OUT OF LINE on purpose: inlined, its
+// register needs disturb the allocation of the register-resident sweep loop of k_solve.
+static __device__ __noinline__ void refine_columns(int n, int npad, int LD, int b, const double* s_Mf, const double* s_invM,
+                                                   const double* s_Lk, double* s_W, double* s_lam, int tid, int nt, bool clean) {
+    (void)clean;
+    for (int s = tid; s < npad; s += nt) {
+        double* w = s_W + s * LD;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+#pragma unroll 2
+        for (; r + 3 < n; r += 4) {
+            a0 = fma(w[r], w[r], a0); a1 = fma(w[r + 1], w[r + 1], a1);
+            a2 = fma(w[r + 2], w[r + 2], a2); a3 = fma(w[r + 3], w[r + 3], a3);
+        }
+        for (; r < n; ++r) a0 = fma(w[r], w[r], a0);
+        const double acc = (a0 + a1) + (a2 + a3);
+        if (acc == 0.0 || !(acc < INFINITY)) {               // the zero dummy column (n odd) sorts last
+            s_lam[s] = (npad != n && acc == 0.0) ? INFINITY : acc;
+            continue;
+        }
+        const double sc = rsqrt_fast(acc);                   // u = sc w, |u| = 1
+        bool flip = false;
+        double lam;
+        if (b <= 5) lam = backsolve_rq<5>(s_Mf, s_invM, s_Lk, w, n, b, sc, flip);
+        else if (b <= 8) lam = backsolve_rq<8>(s_Mf, s_invM, s_Lk, w, n, b, sc, flip);
+        else {                                               // wide bands / dense pencils: plain loops
+            for (int i = 0; i < n; ++i) w[i] *= sc;
+            band_backsolve_thread(s_Mf, s_invM, w, n, b);
+            lam = 0.0;
+            double best = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const int m = min(b, n - 1 - i);
+                double y = 0.0;
+                for (int d = 0; d <= m; ++d) y = fma(s_Lk[d * n + i], w[i + d], y);
+                lam = fma(y, y, lam);
+                const double v = fabs(w[i]);
+                if (v > best) { best = v; flip = w[i] < 0.0; }
+            }
+        }
+        s_lam[s] = lam;
+        if (flip)
+            for (int i = 0; i < n; ++i) w[i] = -w[i];        // sign convention: largest-magnitude entry positive
+    }
+}
+
 // After convergence: eigenvalues (ascending) and the first n_modes shapes to global memory.
 // The columns are sqrt(lam_k) u_k (C u = lam u): shapes phi_k = Lm^-T u_k, back-substituted with the band factor of M
 // passed as s_Kb / s_invK.
-template <int LPP>
-__device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
-                                                   double* s_W, double* s_lam, int* s_order, int n_modes,
-                                                   double* g_lam, double* g_phi, int tid, int nt,
-                                                   bool clean = false, bool compact = false) {
-    const int n = P.n, npad = P.npad, LD = P.LD;
-    // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
-    for (int s = tid; s < npad; s += nt) {
-        double acc = 0.0;
-        const double* w = s_W + s * LD;
-        for (int r = 0; r < n; ++r) acc = fma(w[r], w[r], acc);
-        s_lam[s] = (npad != n && acc == 0.0) ? INFINITY : acc;   // the zero dummy column (n odd) sorts last
+// the plan fields the output stage needs, by value: the stage is kept OUT OF LINE (see below) and must not take the
+// address of the kernel's parameter block
+struct OutDims {
+    int n, npad, LD, hbw, sumdof;
+    const int32_t* free_of_pos;
+};
+
+static __device__ __noinline__ void modal_output_impl(OutDims P, const double* s_Kb, const double* s_invK,
+                                                      double* s_W, double* s_lam, int* s_order, int n_modes,
+                                                      double* g_lam, double* g_phi, int tid, int nt,
+                                                      bool clean, bool compact, const double* s_Lk) {
+    // s_Kb / s_invK: band factor of M (historic names).  s_Lk != nullptr: band factor of K -- every eigenvalue is then
+    // REFINED as the Rayleigh quotient of its shape taken on the two Cholesky factors,
+    //     lam_k = |Lk^T phi_k|^2,  phi_k = Lm^-T u_k,  |u_k| = 1  (phi^T M phi = |Lm^T phi|^2 = 1),
+    // which is second-order accurate in the error of u_k and never sees the rounding of the formed matrix
+    // C = Lm^-1 K Lm^-T or of its pivoted Cholesky factor: the smallest eigenvalues of badly graded pencils gain about
+    // a digit (worst case of the 2.4 M-variant soak: 7e-11 -> see profiles/r2_soak.txt).  One thread per column; the
+    // shapes of ALL columns are formed (the first n_modes of them are the output), which costs latency only.
+    const int n = P.n, npad = P.npad, LD = P.LD, b = P.hbw;
+    if (s_Lk != nullptr) {
+        refine_columns(n, npad, LD, b, s_Kb, s_invK, s_Lk, s_W, s_lam, tid, nt, clean);
+    } else {
+        // squared column norms = eigenvalues; the dummy slot (n odd) sorts last
+        for (int s = tid; s < npad; s += nt) {
+            double acc = 0.0;
+            const double* w = s_W + s * LD;
+            for (int r = 0; r < n; ++r) acc = fma(w[r], w[r], acc);
+            s_lam[s] = (npad != n && acc == 0.0) ? INFINITY : acc;   // the zero dummy column (n odd) sorts last
+        }
     }
     __syncthreads();
     for (int s = tid; s < npad; s += nt) {
@@ -1472,20 +1572,22 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
     }
     __syncthreads();
     if (n_modes <= 0 || g_phi == nullptr) return;
-    // phi = Lk^-T w, in place in the slot; then fix the sign (largest-magnitude entry positive)
-    for (int m = tid; m < n_modes; m += nt) {
-        double* w = s_W + s_order[m] * LD;
-        if (P.hbw <= 8) band_subst<false, true>(s_Kb, s_invK, w, 1, n, P.hbw, 0, clean);
-        else band_backsolve_thread(s_Kb, s_invK, w, n, P.hbw);
-        double best = 0.0, sign = 1.0;
-        for (int r = 0; r < n; ++r) {
-            const double v = fabs(w[r]);
-            if (v > best) { best = v; sign = (w[r] < 0.0) ? -1.0 : 1.0; }
+    if (s_Lk == nullptr) {
+        // phi = Lm^-T w, in place in the slot; then fix the sign (largest-magnitude entry positive)
+        for (int m = tid; m < n_modes; m += nt) {
+            double* w = s_W + s_order[m] * LD;
+            if (b <= 8) band_subst<false, true>(s_Kb, s_invK, w, 1, n, b, 0, clean);
+            else band_backsolve_thread(s_Kb, s_invK, w, n, b);
+            double best = 0.0, sign = 1.0;
+            for (int r = 0; r < n; ++r) {
+                const double v = fabs(w[r]);
+                if (v > best) { best = v; sign = (w[r] < 0.0) ? -1.0 : 1.0; }
+            }
+            sign *= rsqrt_fast(s_lam[s_order[m]]);
+            for (int r = 0; r < n; ++r) w[r] *= sign;
         }
-        sign *= rsqrt_fast(s_lam[s_order[m]]);
-        for (int r = 0; r < n; ++r) w[r] *= sign;
+        __syncthreads();
     }
-    __syncthreads();
     if (compact) {                                       // shapes on the free DOFs only: [n_modes, n]
         for (int t = tid; t < n_modes * n; t += nt) g_phi[t] = s_W[s_order[t / n] * LD + t % n];
         return;
@@ -1495,6 +1597,18 @@ __device__ __forceinline__ void stage_modal_output(const PlanDev& P, const doubl
         const int j = P.free_of_pos[pos];
         g_phi[t] = (j >= 0) ? s_W[s_order[m] * LD + j] : 0.0;
     }
+}
+
+// Out of line on purpose: inlined into k_solve, the output stage changes what ptxas keeps live around the
+// register-resident sweep loop and costs the P20 launch several per cent.
+template <int LPP>
+__device__ __forceinline__ void stage_modal_output(const PlanDev& P, const double* s_Kb, const double* s_invK,
+                                                   double* s_W, double* s_lam, int* s_order, int n_modes,
+                                                   double* g_lam, double* g_phi, int tid, int nt,
+                                                   bool clean = false, bool compact = false,
+                                                   const double* s_Lk = nullptr) {
+    const OutDims d{P.n, P.npad, P.LD, P.hbw, P.sumdof, P.free_of_pos};
+    modal_output_impl(d, s_Kb, s_invK, s_W, s_lam, s_order, n_modes, g_lam, g_phi, tid, nt, clean, compact, s_Lk);
 }
 
 }  // namespace bfe2
