@@ -112,9 +112,9 @@ class SubspaceIteration:
         phi [n_modes, n] M-normalised, iterations, residual [n_modes] = ||K phi - lam M phi||_inf /
         (||K||_max ||phi||_inf), converged)."""
         assert 1 <= n_modes <= Q - 8, 'keep at least 8 guard vectors'
-        g = torch.Generator(device='cpu')
-        g.manual_seed(seed)
-        X = torch.randn((self.n, Q), generator=g, dtype=torch.float64).to(self.device)
+        g = torch.Generator(device=self.device)                 # start block drawn on the device: a host draw + copy of
+        g.manual_seed(seed)                                     # n x 64 doubles cost more than the whole iteration at n = 3e5
+        X = torch.randn((self.n, Q), generator=g, dtype=torch.float64, device=self.device)
         fm = torch.as_tensor(self.fixed_mask.astype(bool), device=self.device)
         X[fm] = 0.0
         Y = self.matvec(X, mass=True)

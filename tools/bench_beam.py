@@ -66,14 +66,17 @@ def main():
                          'rel_err_rot': abs(un[-1] / r_cf - 1),
                          'scaled_residual': float(r.abs().max().item()) / sc,
                          'scaled_residual_double_double_solution': float(rdd.abs().max().item()) / sc}
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    mo = beam.modal(n_modes=args.modes, tol=1e-10, maxit=60)
-    torch.cuda.synchronize()
+    secs = []
+    for _ in range(3):                                   # first call pays lazy library loads; the others are steady state
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mo = beam.modal(n_modes=args.modes, tol=1e-10, maxit=60)
+        torch.cuda.synchronize()
+        secs.append(time.perf_counter() - t0)
     om = np.sqrt(np.maximum(np.nan_to_num(mo['lam'].cpu().numpy(), nan=0.0), 0))
     axial1 = np.pi / 2 * np.sqrt(E / rho) / L
     bend = om[om < 0.99 * axial1][:5]
-    out['gpu_modal'] = {'seconds': time.perf_counter() - t0, 'iterations': mo['iterations'], 'converged': mo['converged'],
+    out['gpu_modal'] = {'seconds': min(secs[1:]), 'seconds_first_call': secs[0], 'iterations': mo['iterations'], 'converged': mo['converged'],
                         'noise_floor': mo['noise_floor'], 'failed': mo['failed'], 'omega_first5_bending': bend.tolist(),
                         'closed_form': w_cf[:5].tolist(),
                         'rel_err_first5': np.abs(bend / w_cf[:len(bend)] - 1).tolist(),
