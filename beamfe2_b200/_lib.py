@@ -14,7 +14,7 @@ SYMBOLS = (
     'bfe2_plan_create', 'bfe2_plan_create_ex', 'bfe2_plan_destroy', 'bfe2_plan_dims', 'bfe2_plan_get_array',
     'bfe2_plan_smem_bytes', 'bfe2_workspace_bytes',
     'bfe2_element_km', 'bfe2_assemble_banded', 'bfe2_static_solve', 'bfe2_modal_solve',
-    'bfe2_solve_fused', 'bfe2_set_modal_engine', 'bfe2_get_modal_engine',
+    'bfe2_solve_fused', 'bfe2_set_modal_engine', 'bfe2_get_modal_engine', 'bfe2_static_tile_launches',
     'bfe2_pattern_create', 'bfe2_pattern_destroy', 'bfe2_pattern_layout', 'bfe2_solve_fused_packed',
     'bfe2_plan_create_dense', 'bfe2_sym_eig_dense',
     'bfe2_beam_create', 'bfe2_beam_create_ex', 'bfe2_beam_destroy', 'bfe2_beam_dims', 'bfe2_beam_solve',
@@ -86,6 +86,8 @@ def lib():
     L.bfe2_set_modal_engine.restype = C.c_int
     L.bfe2_set_modal_engine.argtypes = [i32]
     L.bfe2_get_modal_engine.restype = C.c_int
+    L.bfe2_static_tile_launches.restype = C.c_int64
+    L.bfe2_static_tile_launches.argtypes = []
     L.bfe2_pattern_create.restype = C.c_int
     L.bfe2_pattern_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32, i32, vp, i32, vp]
     L.bfe2_pattern_destroy.restype = None

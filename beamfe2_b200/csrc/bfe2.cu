@@ -15,6 +15,7 @@
 
 #include "../../include/bfe2.h"
 #include "bfe2_device.cuh"
+#include "bfe2_tile.h"
 
 using namespace bfe2;
 
@@ -1586,6 +1587,10 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
     A.u = u; A.endforces = endforces; A.reactions = reactions; A.lam = lam; A.phi = phi;
     A.info = info; A.sweeps = sweeps;
     if (!do_modal) {
+        {   // large batches of narrow-band structures: one lane per structure (bfe2_tile.cu)
+            bfe2_tile_args T{B, C, coords, props, f_nodal, r_local, u, endforces, reactions, info};
+            if (const int r = bfe2_tile_static_launch(pd, T, (cudaStream_t)stream); r <= 0) return r;
+        }
         if (const int r = dispatch_static_group<true>(plan, pd, A, (cudaStream_t)stream); r <= 0) return r;
         PlanDev P = pd;
         P.npad = 0; P.LD = 0;

@@ -154,6 +154,14 @@ int bfe2_solve_fused(bfe2_plan* plan, int64_t B, int32_t C, int32_t do_modal, in
 int bfe2_set_modal_engine(int32_t engine);
 int bfe2_get_modal_engine(void);
 
+/* ---- static-only requests (do_modal = 0) of bfe2_solve_fused run the 16-lanes-per-structure group kernel.  With the
+ *      environment variable BFE2_STATIC_TILE=1 (read once per process) batches of >= 8192 structures
+ *      (BFE2_STATIC_TILE_MIN=<batch> moves the threshold) with half bandwidth <= 5 whose tile fits twice into an SM run
+ *      the one-lane-per-structure tile kernel instead (bfe2_tile.cu) -- same results to rounding, same speed
+ *      (profiles/r2_static_tile.md), kept as a measured experiment.  The counter says how many launches of the tile
+ *      kernel this process has made. */
+int64_t bfe2_static_tile_launches(void);
+
 /* ---- the same fused path on PACKED RECORDS with compact load / result layouts: the end-to-end entry for data
  *      that lives in HOST memory (one copy per direction per chunk; only numbers that carry information travel).
  *      A pattern is created once per (plan, load layout):
