@@ -26,7 +26,8 @@ REF = os.path.join(util.ROOT, 'baseline', '_ref')
 STUB = os.path.join(util.ROOT, 'oracle', 'mpl_stub')
 SHIM = os.path.join(util.ROOT, 'tests', 'refsuite_shim')
 FILES = ['test_beam_linear_elastic.py', 'test_beam_allresults.py', 'test_internal_beamloads.py', 'test_beam_modal.py',
-         'test_beam_buckling.py']
+         'test_beam_buckling.py',
+         'test_beam_sections.py', 'test_material.py']      # off the hot path (the reference's own modules): completeness
 
 # reference test id -> why it cannot pass through this boundary (empty: everything is expected to pass)
 KNOWN_DEVIATIONS = {
@@ -59,7 +60,7 @@ def run_suite(mode):
 def test_reference_tests_run_unchanged_through_the_gpu_boundary(mode):
     passed, failed, out = run_suite(mode)
     print(out[-6000:])
-    assert len(passed) + len(failed) == 47, out[-3000:]          # 24 + 11 + 9 + 2 + 1 reference tests collected
+    assert len(passed) + len(failed) == 57, out[-3000:]          # 24 + 11 + 9 + 2 + 1 on the path, + 10: the whole suite
     unexpected = [t for t in failed if t.split('::', 1)[-1] not in KNOWN_DEVIATIONS[mode]]
     assert not unexpected, '\n'.join(unexpected) + '\n' + out[-6000:]
     stale = [t for t in KNOWN_DEVIATIONS[mode] if not any(f.endswith(t) for f in failed)]
