@@ -40,19 +40,34 @@ class AnalysisResult(object):
 
 
 class LinearStaticResult(AnalysisResult):
-    def __init__(self, structure=None, displacements=None, endforces=None, reactions=None):
+    def __init__(self, structure=None, displacements=None, endforces=None, reactions=None, f_nodal=None):
         super(LinearStaticResult, self).__init__(structure=structure)
         self.displacement_results = displacements
         self.element_end_forces = endforces        # [nE, 6] local end forces from the GPU (K3)
-        self._reactions = reactions                # [sumdof] from the GPU (K3)
+        self._reactions = reactions                # [sumdof] from the GPU (K3): rotated end forces minus f_nodal
+        self._f_nodal = f_nodal                    # [sumdof] the nodal right-hand side the kernel subtracted
 
     @property
     def reaction_forces_asvector(self):
-        """Global reaction vector (sum of rotated beam end forces minus the applied nodal loads)."""
+        """Global reaction vector (sum of rotated beam end forces minus the applied nodal loads).
+
+        The reference subtracts the entries of structure.nodal_loads (Results.py:119-123), i.e. what add_nodal_load
+        recorded -- a load put straight into the load vector with add_single_dynam_to_node is solved for but NOT
+        subtracted.  The kernel subtracts the whole nodal right-hand side; the difference between the two (zero unless
+        add_single_dynam_to_node was called directly) is put back here, at access time like the reference."""
         if not self.solved:
             print('no results available, solve the model first')
             return None
-        return np.array(self._reactions, dtype=np.float64).reshape(-1, 1)
+        out = np.array(self._reactions, dtype=np.float64).reshape(-1, 1)
+        if self._f_nodal is not None:
+            recorded = np.zeros_like(out)
+            for x in self.structure.nodal_loads:
+                pos = self.structure.position_in_matrix(nodeID=x.node.ID, DOF='ux')
+                recorded[pos:pos + 3] += np.asarray(x.asvector, dtype=np.float64).reshape(3, 1)
+            extra = np.asarray(self._f_nodal, dtype=np.float64).reshape(-1, 1) - recorded
+            if np.any(extra):
+                out = out + extra
+        return out
 
     @property
     def reaction_forces(self):

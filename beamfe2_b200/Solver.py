@@ -37,7 +37,9 @@ def _run(structure, static, modal):
         kw.update(nodal_mass=dev(pk['nodal_mass']))
     out = batch.solve_fused(plan, modal=modal, n_modes=plan.n_free if modal else 0, **kw)
     torch.cuda.synchronize()
-    return plan, {k: (v[0].cpu().numpy() if v is not None else None) for k, v in out.items()}
+    host = {k: (v[0].cpu().numpy() if v is not None else None) for k, v in out.items()}
+    host['f_nodal'] = pk['f_nodal'] if static else None
+    return plan, host
 
 
 class LinearStaticSolver(Solver):
@@ -51,7 +53,8 @@ class LinearStaticSolver(Solver):
         disps = np.matrix(out['u'][0]).T                                        # sumdof x 1, zeros at supports
         st.results['linear static'] = Results.LinearStaticResult(structure=st, displacements=[disps],
                                                                  endforces=out['endforces'][0],
-                                                                 reactions=out['reactions'][0])
+                                                                 reactions=out['reactions'][0],
+                                                                 f_nodal=out['f_nodal'][0])
         st.results['linear static'].solved = True
         return True
 
@@ -192,7 +195,7 @@ def solve_structures(structures, static=True, modal=True):
         if do_static and has_load[b] and info <= 0 and np.isfinite(host['u'][b, 0]).all():
             st.results['linear static'] = Results.LinearStaticResult(
                 structure=st, displacements=[np.matrix(host['u'][b, 0]).T], endforces=host['endforces'][b, 0],
-                reactions=host['reactions'][b, 0])
+                reactions=host['reactions'][b, 0], f_nodal=packs[b][1]['f_nodal'][0])
             st.results['linear static'].solved = s_ok = True
         if do_modal and has_mass[b] and info == 0:
             lam = host['lam'][b]

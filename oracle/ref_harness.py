@@ -45,14 +45,14 @@ def reference_available() -> bool:
 
 def install_into_baseline(verbose=False) -> bool:
     """`pip install --target baseline/_ref` of the UNMODIFIED reference (the one offline install the task allows),
-    plus its `drawing` package (BeamFE2 imports it, setup.py does not list it) and its own `Tests/`, so that the
-    reference arm of bench.py and the reference's test-suite can run on the GPU box, where the read-only checkout
+    plus its `drawing` package (BeamFE2 imports it, setup.py does not list it), its own `Tests/` and its `Examples/`
+    scripts, so that the reference arm of bench.py, the reference's test-suite and its examples can run on the GPU box, where the read-only checkout
     does not exist.  baseline/_ref is git-ignored: nothing of the reference enters the history.
     Returns True when baseline/_ref is complete."""
     import shutil
     import subprocess
     import tempfile
-    have = all(os.path.isdir(os.path.join(BASELINE_REF, d)) for d in ('BeamFE2', 'drawing', 'Tests'))
+    have = all(os.path.isdir(os.path.join(BASELINE_REF, d)) for d in ('BeamFE2', 'drawing', 'Tests', 'Examples'))
     if have or not os.path.isdir(os.path.join(REFERENCE_SOURCE, 'BeamFE2')):
         return have
     os.makedirs(BASELINE_REF, exist_ok=True)
@@ -67,7 +67,7 @@ def install_into_baseline(verbose=False) -> bool:
                 sys.stderr.write(r.stdout[-2000:] + r.stderr[-2000:])
             if r.returncode != 0:
                 return False
-    for d in ('drawing', 'Tests'):
+    for d in ('drawing', 'Tests', 'Examples'):
         if not os.path.isdir(os.path.join(BASELINE_REF, d)):
             shutil.copytree(os.path.join(REFERENCE_SOURCE, d), os.path.join(BASELINE_REF, d),
                             ignore=shutil.ignore_patterns('__pycache__'))

@@ -317,3 +317,24 @@ def test_pack_renumbers_wide_bands():
     from beamfe2_b200.plan import Plan
     plain = Plan(24, plan.conn, s.positions_to_eliminate)
     assert plan.hbw <= plain.hbw and sorted(plan.pos_of_free.tolist()) == sorted(plain.pos_of_free.tolist())
+
+
+def test_reactions_subtract_only_recorded_nodal_loads():
+    """Results.py:119-123: the reference subtracts structure.nodal_loads (what add_nodal_load recorded); a load put
+    straight into the load vector with add_single_dynam_to_node (Examples/cantilever_beam_hangman.py) is solved for
+    but not subtracted.  The kernel subtracts the whole nodal right-hand side; the result object puts the
+    unrecorded part back (host logic, no GPU needed: the kernel output is emulated)."""
+    from beamfe2_b200 import Results
+    n1, n2 = Node.Node(ID=1, coords=(0.0, 0.0)), Node.Node(ID=2, coords=(100.0, 0.0))
+    b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=2.1e5, I=22.5, A=30.0, rho=7.85e-9)
+    s = Structure.Structure(beams=[b], supports={1: ['ux', 'uy', 'rotz']})
+    s.add_nodal_load(nodeID=2, dynam={'FX': 7.0}, clear=True)               # recorded
+    s.add_single_dynam_to_node(nodeID=2, dynam={'FY': 100.0})               # load vector only
+    _, pk = s.pack()
+    assert pk['f_nodal'][0].tolist() == [0, 0, 0, 7.0, 100.0, 0]
+    end_forces_global = np.array([-7.0, -100.0, -1e4, 7.0, 100.0, 0.0])     # equilibrium of the cantilever
+    res = Results.LinearStaticResult(structure=s, displacements=[np.matrix(np.zeros((6, 1)))],
+                                     reactions=end_forces_global - pk['f_nodal'][0], f_nodal=pk['f_nodal'][0])
+    res.solved = True
+    assert np.allclose(np.asarray(res.reaction_forces_asvector).ravel(), [-7.0, -100.0, -1e4, 0.0, 100.0, 0.0])
+    assert res.reaction_forces == {1: {'FX': -7.0, 'FY': -100.0, 'MZ': -1e4}}
