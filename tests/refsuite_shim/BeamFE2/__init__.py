@@ -8,6 +8,9 @@ import importlib.util
 import os
 import sys
 
+import numpy as _np
+
+_np.set_printoptions(precision=6, suppress=True, linewidth=250)    # importing the reference does this (BeamFE2/__init__.py:2)
 _REF = os.environ['BFE2_REFERENCE_PACKAGE']
 for _n in ('Node', 'HermitianBeam_2D', 'Structure', 'Solver', 'Results', 'Loads', 'helpers'):
     _m = importlib.import_module('beamfe2_b200.' + _n)
