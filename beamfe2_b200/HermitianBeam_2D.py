@@ -92,6 +92,63 @@ class HermitianBeam2D(object):
     def Ke(self):
         return self._k1(local=True)[0]
 
+    def _Ke(self):
+        return self._k1(local=True)[0]
+
+    def _Me(self):
+        return self._k1(local=True)[1]
+
+    def _Me_lumped(self):
+        """Lumped mass whatever the beam's mass_matrix flag says (HermitianBeam_2D.py:225-231)."""
+        keep, self.mass_matrix = self.mass_matrix, 'lumped'
+        try:
+            return self._k1(local=True)[1]
+        finally:
+            self.mass_matrix = keep
+
+    # ---- cubic Hermite shape functions at the normalised position x in [0, 1] (HermitianBeam_2D.py:176-222); host
+    #      side, used for deflected shapes -- displacement u(x) = N(x) [ux_i, uy_i, rz_i, ux_j, uy_j, rz_j]
+    def N1(self, x, L=1.):
+        return 1 - x
+
+    def N2(self, x, L=1.):
+        return 1 - x * x * (3 - 2 * x)
+
+    def N3(self, x, L=1.):
+        return L * x * (1 - x) ** 2
+
+    def N4(self, x, L=1.):
+        return x
+
+    def N5(self, x, L=1.):
+        return x * x * (3 - 2 * x)
+
+    def N6(self, x, L=1.):
+        return L * x * x * (x - 1)
+
+    def N(self, x, L=1.):
+        out = np.zeros((2, 6))
+        out[0, 0], out[0, 3] = self.N1(x, L), self.N4(x, L)
+        out[1, 1], out[1, 2], out[1, 4], out[1, 5] = self.N2(x, L), self.N3(x, L), self.N5(x, L), self.N6(x, L)
+        return out
+
+    def deflected_shape(self, local=True, scale=1., disps=None):
+        """Points of the deflected axis from the LOCAL end displacements `disps` (6x1), magnified by `scale`, at
+        number_internal_points + 1 stations (HermitianBeam_2D.py:307-334; beam-internal loads not considered).
+        local=True: 2x1 matrices in beam axes; local=False: (x, y) tuples in global axes, starting at node i."""
+        pts = []
+        n = self.number_internal_points
+        R = transfer_matrix(alpha=0 if local else self.direction, asdegree=False, blocks=1, blocksize=2)
+        for k in range(n + 1):
+            v = np.multiply(scale, np.matrix(self.N(x=k / n, L=self.l)) * disps)
+            v[0, 0] += (k / n) * self.l
+            v = R * v
+            if not local:
+                v = np_matrix_tolist(v)
+                v = (v[0] + self.i.x, v[1] + self.i.y)
+            pts.append(v)
+        return pts
+
     @property
     def Me(self):
         assert self.mass_matrix in ['consistent', 'lumped']
@@ -111,7 +168,7 @@ class HermitianBeam2D(object):
     # ---- beam-internal loads
     def add_internal_load(self, loadtype=None, **kwargs):
         assert loadtype in BL.BEAM_LOAD_TYPES
-        self.internal_loads.append(BL.BeamLoad(loadtype=loadtype, beam=self, **kwargs))
+        self.internal_loads.append(BL.LOAD_CLASSES[loadtype](beam=self, **kwargs))
 
     def reduce_internal_load(self, load):
         r = load.reactions

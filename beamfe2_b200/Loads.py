@@ -126,15 +126,19 @@ class BeamLoad(object):
     deflections = property(lambda self: (self.deflection_at_position(x) for x in self.internal_points))
 
 
-def _typed(loadtype):
-    def make(value=None, beam=None, position=0, loadtype=loadtype, **kw):
-        return BeamLoad(loadtype=loadtype, beam=beam, value=value, position=position)
-    return make
+def _typed(name, loadtype):
+    """Subclass with the reference's class name and constructor order (Loads.py:172, 236, 300, 376, 443) whose load
+    type is fixed; all behaviour lives in BeamLoad."""
+    def __init__(self, loadtype=loadtype, value=None, position=0, beam=None, **kw):
+        BeamLoad.__init__(self, loadtype=loadtype, beam=beam, value=value, position=position)
+    return type(name, (BeamLoad,), {'__init__': __init__, '__doc__': '%s acting inside a beam (local system).' % loadtype})
 
 
-# same constructor names as the reference module
-UniformAxialForce = _typed('uniform axial force')
-UniformPerpendicularForce = _typed('uniform perpendicular force')
-ConcentratedPerpendicularForce = _typed('concentrated perpendicular force')
-ConcentratedAxialForce = _typed('concentrated axial force')
-ConcentratedMoment = _typed('concentrated moment')
+UniformAxialForce = _typed('UniformAxialForce', 'uniform axial force')
+UniformPerpendicularForce = _typed('UniformPerpendicularForce', 'uniform perpendicular force')
+ConcentratedPerpendicularForce = _typed('ConcentratedPerpendicularForce', 'concentrated perpendicular force')
+ConcentratedAxialForce = _typed('ConcentratedAxialForce', 'concentrated axial force')
+ConcentratedMoment = _typed('ConcentratedMoment', 'concentrated moment')
+LOAD_CLASSES = {'uniform axial force': UniformAxialForce, 'uniform perpendicular force': UniformPerpendicularForce,
+                'concentrated perpendicular force': ConcentratedPerpendicularForce,
+                'concentrated axial force': ConcentratedAxialForce, 'concentrated moment': ConcentratedMoment}

@@ -14,6 +14,11 @@ import numpy as np
 from . import Loads as BL
 from . import Results, Solver
 from . import plan as planmod
+# the reference does `from BeamFE2.Loads import *` and `from BeamFE2.helpers import *` (Structure.py:3-8): user code
+# reaches these names through the Structure module
+from .Loads import (BEAM_LOAD_TYPES, NODAL_LOAD_TYPES, BeamLoad, ConcentratedAxialForce, ConcentratedMoment,  # noqa: F401
+                    ConcentratedPerpendicularForce, NodalLoad, NodalMass, UniformAxialForce, UniformPerpendicularForce)
+from .helpers import compile_global_matrix, np_matrix_tolist, transfer_matrix  # noqa: F401
 
 VERY_LARGE_NUMBER = 10e40
 
@@ -268,5 +273,11 @@ class Structure(object):
     def compile_global_stiffness_matrix(self):
         return self.K
 
-    def draw(self, *args, **kwargs):
-        print('drawing is outside the accelerated path')
+    def compile_global_geometrical_stiffness_matrix(self):
+        return self.K_geom
+
+    def draw(self, show=True, analysistype=None, mode=0, internal_action=None):
+        if self.results[analysistype].solved:                          # Structure.py:110-114
+            print('drawing is outside the accelerated path')
+        else:
+            print('no results available, no printing')

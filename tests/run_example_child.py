@@ -1,5 +1,5 @@
 """Child process of tests/test_reference_examples.py: runs ONE of the reference's Examples/*.py UNCHANGED, with only
-Structure.draw neutralised (it needs matplotlib; it still triggers the lazy solve the reference's draw() does), and
+Structure.draw neutralised (it needs matplotlib; the 'no results' message of an unsolved analysis is kept), and
 prints what the script left behind as JSON.
 
     python tests/run_example_child.py real|alias|patch <path to example> [--fix]
@@ -28,10 +28,10 @@ if mode == 'patch':
 from BeamFE2 import Structure                      # noqa: E402  (resolved through PYTHONPATH: shim or the real package)
 
 
-def _draw(self, analysistype=None, mode=0, internal_action=None, **kw):
-    # Structure.draw solves on demand before drawing (Structure.py:110-114); keep that side effect
-    if self.results.get(analysistype) is None:
-        self.solver[analysistype].solve()
+def _draw(self, show=True, analysistype=None, mode=0, internal_action=None):
+    # Structure.draw (Structure.py:110-114) draws when the analysis has been solved and says so when not
+    if not self.results[analysistype].solved:
+        print('no results available, no printing')
 
 
 Structure.Structure.draw = _draw

@@ -338,3 +338,35 @@ def test_reactions_subtract_only_recorded_nodal_loads():
     res.solved = True
     assert np.allclose(np.asarray(res.reaction_forces_asvector).ravel(), [-7.0, -100.0, -1e4, 0.0, 100.0, 0.0])
     assert res.reaction_forces == {1: {'FX': -7.0, 'FY': -100.0, 'MZ': -1e4}}
+
+
+def test_shape_functions_and_load_classes_match_the_reference():
+    """Host-side helpers a user script may touch: Hermite shape functions / deflected shape
+    (HermitianBeam_2D.py:176-222, 307-334) and the named beam-load classes (Loads.py:163-502) -- against the real
+    reference when it is installed."""
+    n1, n2 = Node.Node(ID=1, coords=(10.0, -5.0)), Node.Node(ID=2, coords=(40.0, 35.0))
+    b = HB.HermitianBeam2D(ID=1, i=n1, j=n2, E=2.1e5, I=22.5, A=30.0, rho=7.85e-9)
+    L = b.l
+    for x in (0.0, 0.3, 1.0):
+        assert np.allclose(b.N(x, L)[:, [0, 3]].sum(), 1.0) and math.isclose(b.N2(x, L) + b.N5(x, L), 1.0)
+    assert b.N3(0.0, L) == b.N6(1.0, L) == 0.0
+    h = 1e-6                                                    # end slopes: N3'(0) = N6'(1) = 1 (per unit of x L)
+    assert math.isclose(b.N3(h, L) / (h * L), 1.0, rel_tol=1e-5) and math.isclose(-b.N6(1 - h, L) / (h * L), 1.0, rel_tol=1e-5)
+    ld = Loads.ConcentratedMoment(value=3.0, position=0.25, beam=b)
+    assert isinstance(ld, Loads.BeamLoad) and ld.loadtype == 'concentrated moment' and ld.position == 0.25
+    b.add_internal_load(loadtype='uniform axial force', value=2.0)
+    assert isinstance(b.internal_loads[-1], Loads.UniformAxialForce) and Structure.UniformAxialForce is Loads.UniformAxialForce
+    if not rh.reference_available():
+        return
+    ref = rh.import_reference()
+    rb = ref.HermitianBeam_2D.HermitianBeam2D(ID=1, i=ref.Node.Node(ID=1, coords=(10.0, -5.0)),
+                                              j=ref.Node.Node(ID=2, coords=(40.0, 35.0)), E=2.1e5, I=22.5, A=30.0,
+                                              rho=7.85e-9)
+    for x in (0.0, 0.17, 0.5, 0.99, 1.0):
+        assert np.allclose(b.N(x=x, L=L), rb.N(x=x, L=L), rtol=1e-13, atol=1e-13)
+    d = np.matrix([[0.1], [0.2], [0.003], [-0.05], [0.4], [-0.002]])
+    for local in (True, False):
+        mine, theirs = b.deflected_shape(local=local, scale=3.0, disps=d), rb.deflected_shape(local=local, scale=3.0, disps=d)
+        assert len(mine) == len(theirs)
+        for p, q in zip(mine, theirs):
+            assert np.allclose(np.asarray(p, dtype=float).ravel(), np.asarray(q, dtype=float).ravel(), rtol=1e-12, atol=1e-12)
