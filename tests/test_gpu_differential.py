@@ -119,6 +119,9 @@ def test_random_api_sequences_agree_with_the_reference(seed):
     # ---- matrices (GPU element + assembly kernels vs the reference's numpy)
     for name in ('K', 'M', 'M_with_masses', 'K_with_BC'):
         assert rel(getattr(mine, name), getattr(theirs, name)) < 5e-14, name
+    for name in ('node_numbering_is_ok', 'stiffness_matrix_is_symmetric', 'stiffness_matrix_is_nonsingular',
+                 'stiffness_matrix_is_ok', 'mass_matrix_is_ok'):
+        assert getattr(mine, name) is True and getattr(theirs, name) is True, name
     Kc = arr(theirs.condense(theirs.K))
     tol = max(1e-9, 100 * EPS * np.linalg.cond(Kc))              # the reference inverts the penalty matrix
     # ---- static
