@@ -654,3 +654,44 @@ def test_two_ended_engine_vs_jacobi_and_repair_path():
     # more shapes than the two-ended engine returns: routed to Jacobi whatever the setting
     many = batch.solve_fused(plan, pk['coords'][:16], pk['props'][:16], pk['nodal_mass'][:16], None, None, n_modes=30)
     assert (many['sweeps'] > 0).all() and (many['info'] == 0).all()
+
+
+@pytest.mark.parametrize('packed', [False, True])
+def test_change_of_units_is_only_a_change_of_units(packed):
+    """Dimensional consistency (no hidden absolute threshold anywhere on the path): the P20 batch in N-mm-t units and the
+    same structures in SI (m, Pa, kg/m^3, N) must give the same frequencies, and displacements / end forces / reactions
+    that differ by the unit factors only -- to rounding, although every intermediate number differs by 3 to 12 decades."""
+    _, pk, plan = p20_batch(256)
+    si = dict(coords=pk['coords'] * 1e-3,
+              props=pk['props'] * torch.tensor([1e6, 1e-6, 1e-12, 1e12], dtype=torch.float64, device=DEV),
+              nodal_mass=pk['nodal_mass'] * 1e3,                       # t -> kg
+              f_nodal=pk['f_nodal'].clone(), r_local=pk['r_local'].clone())
+    si['f_nodal'][..., 2::3] *= 1e-3                                   # moments N mm -> N m
+    si['r_local'][..., 2::3] *= 1e-3
+    if packed:
+        def solve(d):
+            io = batch.PackedIO.from_dense(plan, d['f_nodal'], d['r_local'], n_modes=10)
+            rec = torch.zeros((d['coords'].shape[0], io.w_in), dtype=torch.float64, device=DEV)
+            io.pack_inputs(rec, d['coords'], d['props'], d['nodal_mass'], d['f_nodal'], d['r_local'])
+            return io.expand(io.out_views(io.solve(rec)))
+    else:
+        def solve(d):
+            return batch.solve_fused(plan, d['coords'], d['props'], d['nodal_mass'], d['f_nodal'], d['r_local'], n_modes=10)
+    a, b = solve(pk), solve(si)
+    assert int(a['info'].abs().max()) == 0 and int(b['info'].abs().max()) == 0
+    assert torch.equal(a['sweeps'], b['sweeps']) or (a['sweeps'] - b['sweeps']).abs().max() <= 1
+    assert float((b['lam'] / a['lam'] - 1).abs().max()) < 1e-10
+    uf = torch.tensor([1e-3, 1e-3, 1.0], dtype=torch.float64, device=DEV).repeat(21)          # ux, uy [m], rotz [rad]
+    ff = torch.tensor([1.0, 1.0, 1e-3], dtype=torch.float64, device=DEV)
+    for key, fac in (('u', uf), ('reactions', ff.repeat(21)), ('endforces', ff.repeat(2))):
+        x, y = a[key] * fac, b[key]
+        scale = (x.abs() / fac).amax(dim=-1, keepdim=True) * fac       # per structure and load case, per unit class
+        assert float(((x - y).abs() / scale.clamp_min(1e-300)).max()) < 1e-9, key
+    # M-normalised shapes: phi = u / q with q in sqrt(mass) x length -> translations x sqrt(t / kg), rotations x 1e3 more
+    pf = torch.tensor([1.0, 1.0, 1e3], dtype=torch.float64, device=DEV).repeat(21) * np.sqrt(1e-3)
+    phi_a, phi_b = a['phi'] * pf, b['phi']
+    sgn = torch.sign((phi_a * phi_b).sum(dim=-1, keepdim=True))
+    gap_ok = ((a['lam'][:, 1:11] - a['lam'][:, :10]) / a['lam'][:, 1:11] > 1e-3) & \
+        torch.cat([torch.ones_like(a['lam'][:, :1], dtype=torch.bool), (a['lam'][:, 1:10] - a['lam'][:, :9]) / a['lam'][:, 1:10] > 1e-3], 1)
+    err = (phi_a * sgn - phi_b).abs().amax(dim=-1) / phi_b.abs().amax(dim=-1)
+    assert float(err[gap_ok].max()) < 1e-7
