@@ -695,3 +695,22 @@ def test_change_of_units_is_only_a_change_of_units(packed):
         torch.cat([torch.ones_like(a['lam'][:, :1], dtype=torch.bool), (a['lam'][:, 1:10] - a['lam'][:, :9]) / a['lam'][:, 1:10] > 1e-3], 1)
     err = (phi_a * sgn - phi_b).abs().amax(dim=-1) / phi_b.abs().amax(dim=-1)
     assert float(err[gap_ok].max()) < 1e-7
+
+
+@pytest.mark.parametrize('modal', [False, True])
+def test_superposition_of_load_cases_at_full_size(modal):
+    """Linearity at config-3 size (1e5 variants, no CPU solve): with load case 3 := load case 1 + load case 2 (nodal
+    loads and beam loads), displacements, end forces and reactions of case 3 are the sums -- on the static-only
+    kernel and on the fused static + modal kernel."""
+    B = 100000
+    _, pk, plan = p20_batch(B)
+    f, r = pk['f_nodal'].clone(), pk['r_local'].clone()
+    f[:, 2] = f[:, 0] + f[:, 1]
+    r[:, 2] = r[:, 0] + r[:, 1]
+    out = batch.solve_fused(plan, pk['coords'], pk['props'], pk['nodal_mass'] if modal else None, f, r, modal=modal,
+                            n_modes=3 if modal else None)
+    assert (out['info'] == 0).all()
+    for key in ('u', 'endforces', 'reactions'):
+        x = out[key].reshape(B, 3, -1)
+        scale = x.abs().amax(dim=(1, 2))
+        assert float(((x[:, 0] + x[:, 1] - x[:, 2]).abs().amax(dim=1) / scale).max()) < 1e-11, key
