@@ -172,7 +172,14 @@ def test_random_api_sequences_agree_with_the_reference(seed):
         return np.array(out)
     res_m, res_t = residuals(mm, fa), residuals(mt, fb)
     lumped = any(b.mass_matrix == 'lumped' for b in theirs.beams)
-    assert len(fa) == len(keep) and (res_m < (1e-3 if lumped else 1e-8)).all(), res_m
+    assert len(fa) == len(keep)
+    if lumped:
+        # a residual cannot be EVALUATED in double precision on such a pencil (|K v| for a low mode is 1e-18 of
+        # |K| |v|): the judge is a 60-digit solution of the same double-precision matrices, for every mode
+        ft = np.sqrt(util.truth_eigenvalues(Kc, Mc)) / (2 * np.pi)
+        assert np.abs(fa / ft - 1).max() < 1e-9, np.abs(fa / ft - 1)
+    else:
+        assert (res_m < 1e-8).all(), res_m
     assert np.allclose(mm.periods, 1.0 / fa) and len(mm.displacement_results) == len(keep)
     if not lumped:
         assert len(fb) == len(fa) and (res_t < 1e-6).all()
@@ -188,3 +195,17 @@ def test_random_api_sequences_agree_with_the_reference(seed):
     for k in range(len(fa)):
         v = arr(mm.modeshape(k)).ravel()
         assert abs(v @ Mfull @ v - 1) < 1e-8
+
+
+def test_patched_reference_agrees_with_itself():
+    """The same random models through the unmodified reference and through the reference with only its two solve()
+    bodies replaced by the ctypes stub (INTEGRATION.md option B) -- in a child process, because the patch is global."""
+    import os
+    import subprocess
+    import sys
+    if not rh.reference_available():
+        pytest.skip('baseline/_ref is not installed')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=util.ROOT)
+    r = subprocess.run([sys.executable, '-m', 'tests.differential_patch_child', '24'], cwd=util.ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and 'OK 24 models' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

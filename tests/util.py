@@ -114,3 +114,20 @@ def refined_eigenvalues(Kc, Mc, V):
     K, M, V = Kc.astype(np.longdouble), Mc.astype(np.longdouble), V.astype(np.longdouble)
     rq = np.einsum('bmi,bij,bmj->bm', V, K, V) / np.einsum('bmi,bij,bmj->bm', V, M, V)
     return rq.astype(np.float64)
+
+
+def truth_eigenvalues(Kc, Mc, dps=60):
+    """All eigenvalues (ascending, as floats) of the symmetric-definite pencil (Kc, Mc) from a `dps`-digit mpmath
+    solution -- for small pencils whose grading (lam_max / lam_min up to 1e20 with the reference's lumped mass) puts
+    them beyond what any double-precision comparator resolves."""
+    import mpmath as mp
+    old = mp.mp.dps
+    mp.mp.dps = dps
+    try:
+        K, M = mp.matrix(np.asarray(Kc).tolist()), mp.matrix(np.asarray(Mc).tolist())
+        Li = mp.inverse(mp.cholesky(M))
+        Cm = Li * K * Li.T
+        E = mp.eigsy((Cm + Cm.T) / 2, eigvals_only=True)
+        return np.array(sorted(float(e) for e in E))
+    finally:
+        mp.mp.dps = old
