@@ -1473,9 +1473,9 @@ size_t bfe2_workspace_bytes(const bfe2_plan*, int64_t) { return 0; }
 int bfe2_element_km(int64_t nE, const double* xi, const double* yi, const double* xj, const double* yj,
                     const double* E, const double* A, const double* I, const double* rho,
                     const uint8_t* lumped, double* Kg, double* Mg, void* stream) {
+    if (nE == 0) return 0;                        // empty arrays may come with NULL pointers
     if (nE < 0 || !xi || !yi || !xj || !yj || !E || !A || !I || !rho || !Kg || !Mg)
         return fail(-1, "bfe2_element_km: NULL argument");
-    if (nE == 0) return 0;
     int dev = 0, sms = 0;
     BFE2_CUDA(cudaGetDevice(&dev));
     BFE2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

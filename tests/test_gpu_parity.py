@@ -714,3 +714,30 @@ def test_superposition_of_load_cases_at_full_size(modal):
         x = out[key].reshape(B, 3, -1)
         scale = x.abs().amax(dim=(1, 2))
         assert float(((x[:, 0] + x[:, 1] - x[:, 2]).abs().amax(dim=1) / scale).max()) < 1e-11, key
+
+
+def test_every_entry_point_accepts_an_empty_batch():
+    """B = 0 (an empty shard of a ragged split, tests/test_dist_gloo.py) is legal everywhere: outputs of the right
+    shape, no launch, no error."""
+    _, pk, plan = p20_batch(4)
+    z = {k: v[:0] for k, v in pk.items()}
+    Kb, Mb = batch.assemble_banded(plan, z['coords'], z['props'], z['nodal_mass'])
+    assert Kb.shape == (0, plan.hbw + 1, plan.n_free) and Mb.shape == Kb.shape
+    st = batch.static_solve(plan, Kb, z['coords'], z['props'], z['f_nodal'], z['r_local'])
+    assert st['u'].shape == (0, 3, 63) and st['endforces'].shape == (0, 3, 20, 6) and st['info'].shape == (0,)
+    mo = batch.modal_solve(plan, Kb, Mb, n_modes=10)
+    assert mo['lam'].shape == (0, 57) and mo['phi'].shape == (0, 10, 63)
+    for modal in (False, True):
+        out = batch.solve_fused(plan, z['coords'], z['props'], z['nodal_mass'], z['f_nodal'], z['r_local'], modal=modal,
+                                n_modes=10 if modal else None)
+        assert out['u'].shape == (0, 3, 63) and out['reactions'].shape == (0, 3, 63)
+    io = batch.PackedIO.from_dense(plan, pk['f_nodal'], pk['r_local'], n_modes=10)
+    rec = torch.zeros((0, io.w_in), dtype=torch.float64, device=DEV)
+    v = io.out_views(io.solve(rec))
+    assert v['lam'].shape == (0, 57) and v['info'].shape == (0,)
+    e = torch.zeros(0, dtype=torch.float64, device=DEV)
+    Kg, Mg = batch.element_km(e, e, e, e, e, e, e, e)
+    assert Kg.shape == (0, 6, 6) and Mg.shape == (0, 6, 6)
+    act, mx = batch.internal_actions(plan, z['coords'], st['endforces'], None, None, npts=5)
+    assert act.shape[0] == 0 and mx.shape[0] == 0
+    torch.cuda.synchronize()
