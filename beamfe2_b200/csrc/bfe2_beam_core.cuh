@@ -14,6 +14,19 @@ namespace bfe2 {
 namespace chain {
 
 // ---- 3x3 helpers (row-major) ------------------------------------------------------------------
+// software prefetch of a line into L1 (device only): the sequential chains below are bound by one memory round trip
+// per step unless the operands of the steps ahead are already on their way
+#ifdef __CUDA_ARCH__
+#define BFE2_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#else
+#define BFE2_PREFETCH(ptr) ((void)0)
+#endif
+constexpr int PF_AHEAD = 3;                       // steps of look-ahead
+template <class S> BFE2_HD void m3_prefetch(const S* p) {      // a 3 x 3 block: 72 or 144 bytes, up to three lines
+    BFE2_PREFETCH(p);
+    BFE2_PREFETCH(p + 4);
+    BFE2_PREFETCH(p + 8);
+}
 template <class S> BFE2_HD void m3_load(S a[9], const S* p) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) a[i] = p[i];
@@ -201,6 +214,10 @@ BFE2_HD int factor_partition(int a, int b, const S* Kd, const S* Kl, S* Sinv, S*
     S Sk[9], Si[9], Lk[9], Gk[9], Tm[9];
     m3_load(Sk, Kd + 9 * (long long)a);
     for (int k = a; k <= b; ++k) {
+        if (k + PF_AHEAD < b) {
+            m3_prefetch(Kl + 9 * (long long)(k + PF_AHEAD));
+            m3_prefetch(Kd + 9 * (long long)(k + PF_AHEAD + 1));
+        }
         if (!m3_spd_inv(Si, Sk)) return k + 1;
         m3_store(Sinv + 9 * (long long)k, Si);
         if (k < b) {
@@ -223,17 +240,20 @@ template <> struct MVec<double> {
     double* hi; double* lo; long long nrhs;
     BFE2_HD double get(long long i) const { return hi[i]; }
     BFE2_HD void put(long long i, double v) const { hi[i] = v; }
+    BFE2_HD void prefetch(long long i) const { BFE2_PREFETCH(hi + i); }
 };
 template <> struct MVec<dd> {
     double* hi; double* lo; long long nrhs;
     BFE2_HD dd get(long long i) const { return dd{hi[i], lo ? lo[i] : 0.0}; }
     BFE2_HD void put(long long i, dd v) const { hi[i] = v.hi; lo[i] = v.lo; }
+    BFE2_HD void prefetch(long long i) const { BFE2_PREFETCH(hi + i); if (lo) BFE2_PREFETCH(lo + i); }
 };
 // one column of a spike block array: element (node k, dof d) at base[9 k + 3 d]
 template <class S> struct SpikeCol {
     S* base;
     BFE2_HD S get(long long i) const { return base[i]; }
     BFE2_HD void put(long long i, S v) const { base[i] = v; }
+    BFE2_HD void prefetch(long long i) const { BFE2_PREFETCH(base + i); }
 };
 
 // solve T y = w in place for one column: y(node k, dof d) at index k*nstride + d*stride + off of `acc`
@@ -244,26 +264,43 @@ BFE2_HD void part_solve_inplace(const Acc& acc, long long off, long long nstride
     // forward: w_k = f_k - G_{k-1} w_{k-1}
     for (int d = 0; d < 3; ++d) w[d] = acc.get(off + a * nstride + d * stride);
     for (int k = a + 1; k <= b; ++k) {
+        if (k + PF_AHEAD <= b) {
+            m3_prefetch(G + 9 * (long long)(k + PF_AHEAD - 1));
+            for (int d = 0; d < 3; ++d) acc.prefetch(off + (k + PF_AHEAD) * nstride + d * stride);
+        }
         m3_load(g, G + 9 * (long long)(k - 1));
-        m3_vec(t, g, w);
         const long long o = off + k * nstride;
         for (int d = 0; d < 3; ++d) {
-            w[d] = acc.get(o + d * stride) - t[d];
+            DotAcc<S> s3;
+            s3.init(acc.get(o + d * stride));
+            for (int j = 0; j < 3; ++j) s3.sub(g[3 * d + j], w[j]);
+            t[d] = s3.get();
+        }
+        for (int d = 0; d < 3; ++d) {
+            w[d] = t[d];
             acc.put(o + d * stride, w[d]);
         }
     }
     // diagonal + backward: y_k = S_k^-1 w_k - G_k^T y_{k+1}
     S y[3];
     for (int k = b; k >= a; --k) {
+        if (k - PF_AHEAD >= a) {
+            m3_prefetch(Sinv + 9 * (long long)(k - PF_AHEAD));
+            m3_prefetch(G + 9 * (long long)(k - PF_AHEAD));
+            for (int d = 0; d < 3; ++d) acc.prefetch(off + (k - PF_AHEAD) * nstride + d * stride);
+        }
         const long long o = off + k * nstride;
         for (int d = 0; d < 3; ++d) w[d] = acc.get(o + d * stride);
         m3_load(g, Sinv + 9 * (long long)k);
-        S v[3];
-        m3_vec(v, g, w);
-        if (k < b) {
-            m3_load(g, G + 9 * (long long)k);
-            m3_vec_t(t, g, y);
-            for (int d = 0; d < 3; ++d) v[d] = v[d] - t[d];
+        S v[3], gt[9];
+        if (k < b) m3_load(gt, G + 9 * (long long)k);
+        for (int d = 0; d < 3; ++d) {
+            DotAcc<S> s3;
+            s3.init(sc<S>::make(0.0));
+            for (int j = 0; j < 3; ++j) s3.add(g[3 * d + j], w[j]);
+            if (k < b)
+                for (int j = 0; j < 3; ++j) s3.sub(gt[3 * j + d], y[j]);
+            v[d] = s3.get();
         }
         for (int d = 0; d < 3; ++d) {
             y[d] = v[d];
@@ -346,35 +383,58 @@ BFE2_HD void solve_reduced_rhs(int P, int r, const int* sep, const S* Kl, const 
     S g[3], t[3], A[9], y[3], w[3];
     for (int d = 0; d < 3; ++d) w[d] = T::make(0.0);
     for (int j = 0; j < P - 1; ++j) {
+        if (j + PF_AHEAD < P - 1) {
+            const long long s2 = sep[j + PF_AHEAD + 1];
+            for (int d = 0; d < 3; ++d) {
+                U.prefetch(s2 * ns + r + d * nrhs);
+                U.prefetch((s2 - 1) * ns + r + d * nrhs);
+                U.prefetch((s2 + 1) * ns + r + d * nrhs);
+            }
+            m3_prefetch(Kl + 9 * (s2 - 1));
+            m3_prefetch(Kl + 9 * s2);
+            m3_prefetch(RG + 9 * (long long)(j + PF_AHEAD - 1));
+        }
         const long long s = sep[j + 1];
         const long long os = s * ns + r, om = (s - 1) * ns + r, op = (s + 1) * ns + r;
-        for (int d = 0; d < 3; ++d) { g[d] = U.get(os + d * nrhs); y[d] = U.get(om + d * nrhs); }
-        m3_load(A, Kl + 9 * (s - 1));
-        m3_vec(t, A, y);                               // L[s-1] y[s-1]
-        for (int d = 0; d < 3; ++d) { g[d] = g[d] - t[d]; y[d] = U.get(op + d * nrhs); }
-        m3_load(A, Kl + 9 * s);
-        m3_vec_t(t, A, y);                             // L[s]^T y[s+1]
-        for (int d = 0; d < 3; ++d) g[d] = g[d] - t[d];
-        if (j > 0) {
-            m3_load(A, RG + 9 * (j - 1));
-            m3_vec(t, A, w);                           // RG_{j-1} w_{j-1}
-            for (int d = 0; d < 3; ++d) g[d] = g[d] - t[d];
+        S yp[3], A2[9], A3[9];
+        for (int d = 0; d < 3; ++d) { g[d] = U.get(os + d * nrhs); y[d] = U.get(om + d * nrhs); yp[d] = U.get(op + d * nrhs); }
+        m3_load(A, Kl + 9 * (s - 1));                  // L[s-1] y[s-1]
+        m3_load(A2, Kl + 9 * s);                       // L[s]^T y[s+1]
+        if (j > 0) m3_load(A3, RG + 9 * (j - 1));      // RG_{j-1} w_{j-1}
+        for (int d = 0; d < 3; ++d) {
+            DotAcc<S> s3;
+            s3.init(g[d]);
+            for (int i = 0; i < 3; ++i) s3.sub(A[3 * d + i], y[i]);
+            for (int i = 0; i < 3; ++i) s3.sub(A2[3 * i + d], yp[i]);
+            if (j > 0)
+                for (int i = 0; i < 3; ++i) s3.sub(A3[3 * d + i], w[i]);
+            t[d] = s3.get();
         }
+        for (int d = 0; d < 3; ++d) g[d] = t[d];
         for (int d = 0; d < 3; ++d) { w[d] = g[d]; U.put(os + d * nrhs, w[d]); }
     }
     S x[3];
     for (int d = 0; d < 3; ++d) x[d] = T::make(0.0);
     for (int j = P - 2; j >= 0; --j) {
+        if (j - PF_AHEAD >= 0) {
+            const long long s2 = sep[j - PF_AHEAD + 1];
+            for (int d = 0; d < 3; ++d) U.prefetch(s2 * ns + r + d * nrhs);
+            m3_prefetch(RSinv + 9 * (long long)(j - PF_AHEAD));
+            m3_prefetch(RG + 9 * (long long)(j - PF_AHEAD));
+        }
         const long long s = sep[j + 1];
         const long long os = s * ns + r;
         for (int d = 0; d < 3; ++d) w[d] = U.get(os + d * nrhs);
-        S v[3];
+        S v[3], A2[9];
         m3_load(A, RSinv + 9 * j);
-        m3_vec(v, A, w);
-        if (j < P - 2) {
-            m3_load(A, RG + 9 * j);
-            m3_vec_t(t, A, x);
-            for (int d = 0; d < 3; ++d) v[d] = v[d] - t[d];
+        if (j < P - 2) m3_load(A2, RG + 9 * j);
+        for (int d = 0; d < 3; ++d) {
+            DotAcc<S> s3;
+            s3.init(T::make(0.0));
+            for (int i = 0; i < 3; ++i) s3.add(A[3 * d + i], w[i]);
+            if (j < P - 2)
+                for (int i = 0; i < 3; ++i) s3.sub(A2[3 * i + d], x[i]);
+            v[d] = s3.get();
         }
         for (int d = 0; d < 3; ++d) { x[d] = v[d]; U.put(os + d * nrhs, x[d]); }
     }
@@ -387,19 +447,25 @@ BFE2_HD void solve_fix_node(long long k, int r, int p, long long N, const int* s
     const long long nrhs = U.nrhs, ns = 3 * nrhs;
     const long long sl = sep[p], sr = sep[p + 1];
     const long long o = k * ns + r;
-    S y[3], A[9], x[3], tt[3];
+    S y[3], A[9], B[9], xl[3], xr[3];
+    const bool left = sl >= 0, right = sr < N;
     for (int d = 0; d < 3; ++d) y[d] = U.get(o + d * nrhs);
-    if (sl >= 0) {
-        for (int d = 0; d < 3; ++d) x[d] = U.get(sl * ns + r + d * nrhs);
+    if (left) {
+        for (int d = 0; d < 3; ++d) xl[d] = U.get(sl * ns + r + d * nrhs);
         m3_load(A, Vl + 9 * k);
-        m3_vec(tt, A, x);
-        for (int d = 0; d < 3; ++d) y[d] = y[d] - tt[d];
     }
-    if (sr < N) {
-        for (int d = 0; d < 3; ++d) x[d] = U.get(sr * ns + r + d * nrhs);
-        m3_load(A, Vr + 9 * k);
-        m3_vec(tt, A, x);
-        for (int d = 0; d < 3; ++d) y[d] = y[d] - tt[d];
+    if (right) {
+        for (int d = 0; d < 3; ++d) xr[d] = U.get(sr * ns + r + d * nrhs);
+        m3_load(B, Vr + 9 * k);
+    }
+    for (int d = 0; d < 3; ++d) {
+        DotAcc<S> s3;
+        s3.init(y[d]);
+        if (left)
+            for (int i = 0; i < 3; ++i) s3.sub(A[3 * d + i], xl[i]);
+        if (right)
+            for (int i = 0; i < 3; ++i) s3.sub(B[3 * d + i], xr[i]);
+        y[d] = s3.get();
     }
     for (int d = 0; d < 3; ++d) U.put(o + d * nrhs, y[d]);
 }
@@ -412,21 +478,27 @@ BFE2_HD void matvec_node(long long k, int r, long long N, const S* D, const S* L
                          const double* F, double* Y) {
     typedef sc<S> T;
     const long long nrhs = X.nrhs, ns = 3 * nrhs;
-    S A[9], x[3], y[3], tt[3];
+    S A[9], Am[9], Ap[9], x[3], xm[3], xp[3], y[3];
+    const bool lower = k > 0, upper = k < N - 1;
     for (int d = 0; d < 3; ++d) x[d] = X.get(k * ns + r + d * nrhs);
     m3_load(A, D + 9 * k);
-    m3_vec(y, A, x);
-    if (k > 0) {
-        for (int d = 0; d < 3; ++d) x[d] = X.get((k - 1) * ns + r + d * nrhs);
-        m3_load(A, Lb + 9 * (k - 1));
-        m3_vec(tt, A, x);
-        for (int d = 0; d < 3; ++d) y[d] = y[d] + tt[d];
+    if (lower) {
+        for (int d = 0; d < 3; ++d) xm[d] = X.get((k - 1) * ns + r + d * nrhs);
+        m3_load(Am, Lb + 9 * (k - 1));
     }
-    if (k < N - 1) {
-        for (int d = 0; d < 3; ++d) x[d] = X.get((k + 1) * ns + r + d * nrhs);
-        m3_load(A, Lb + 9 * k);
-        m3_vec_t(tt, A, x);
-        for (int d = 0; d < 3; ++d) y[d] = y[d] + tt[d];
+    if (upper) {
+        for (int d = 0; d < 3; ++d) xp[d] = X.get((k + 1) * ns + r + d * nrhs);
+        m3_load(Ap, Lb + 9 * k);
+    }
+    for (int d = 0; d < 3; ++d) {
+        DotAcc<S> s3;
+        s3.init(T::make(0.0));
+        for (int i = 0; i < 3; ++i) s3.add(A[3 * d + i], x[i]);
+        if (lower)
+            for (int i = 0; i < 3; ++i) s3.add(Am[3 * d + i], xm[i]);
+        if (upper)
+            for (int i = 0; i < 3; ++i) s3.add(Ap[3 * i + d], xp[i]);
+        y[d] = s3.get();
     }
     for (int d = 0; d < 3; ++d) {
         const long long o = k * ns + r + d * nrhs;

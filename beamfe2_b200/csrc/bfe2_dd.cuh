@@ -106,6 +106,34 @@ BFE2_HD dd operator*(double a, dd b) { return dd_mul_d(b, a); }
 BFE2_HD dd& operator+=(dd& a, dd b) { a = dd_add(a, b); return a; }
 BFE2_HD dd& operator-=(dd& a, dd b) { a = dd_sub(a, b); return a; }
 
+// ---- running sum of products  f +- a1 b1 +- a2 b2 ...  with ONE renormalisation at the end ---------------------
+//   s carries the leading part through error-free two_sums; every error term and every low-order part of a product
+//   is collected in e.  Those parts are 2^-53 of their terms, so adding them in FP64 costs 2^-106 relative to the
+//   largest term: the accuracy of the same sum written as a chain of dd_mul / dd_add, at a quarter of the operations
+//   and a fifth of the dependent depth (the chain kernels are latency bound: profiles/r2_config4_partitions.txt).
+template <class S> struct DotAcc;
+template <> struct DotAcc<double> {
+    double v;
+    BFE2_HD void init(double f) { v = f; }
+    BFE2_HD void add(double a, double b) { v = BFE2_FMA(a, b, v); }
+    BFE2_HD void sub(double a, double b) { v = BFE2_FMA(-a, b, v); }
+    BFE2_HD double get() const { return v; }
+};
+template <> struct DotAcc<dd> {
+    double s, e;
+    BFE2_HD void init(dd f) { s = f.hi; e = f.lo; }
+    BFE2_HD void add(dd a, dd b) {
+        double p, q, t, r;
+        two_prod(a.hi, b.hi, p, q);
+        q = BFE2_ADD(q, BFE2_FMA(a.hi, b.lo, BFE2_MUL(a.lo, b.hi)));
+        two_sum(s, p, t, r);
+        s = t;
+        e = BFE2_ADD(e, BFE2_ADD(r, q));
+    }
+    BFE2_HD void sub(dd a, dd b) { add(dd{-a.hi, -a.lo}, b); }
+    BFE2_HD dd get() const { dd r; two_sum(s, e, r.hi, r.lo); return r; }
+};
+
 // ---- scalar traits: the chain kernels are templates over S = double (plain FP64) or S = dd ------------------
 template <class S> struct sc;
 template <> struct sc<double> {
