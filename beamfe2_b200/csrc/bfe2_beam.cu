@@ -13,8 +13,10 @@
 //     (scipy.linalg.solveh_banded) is a dependency chain of length n.  Here the chain is cut into P
 //     partitions separated by single nodes (SPIKE / substructuring): every partition is block-Cholesky
 //     factorised independently, its two "spikes" T^-1 E_left, T^-1 E_right give the Schur complement on the
-//     P-1 separator nodes (again block tridiagonal, solved sequentially, P-1 steps), then the interiors are
-//     corrected.  All right-hand sides are processed in parallel (thread per (partition, rhs)).
+//     P-1 separator nodes (again block tridiagonal), then the interiors are corrected.  The separator system is
+//     either eliminated sequentially (one level, P-1 steps) or -- two levels, automatic for long chains -- cut into
+//     partitions once more, so that a solve walks three chains of ~cbrt(N) steps instead of two of ~sqrt(N).
+//     All right-hand sides are processed in parallel (thread per (partition, rhs)).
 //   * Modal: shift-invert (sigma = 0) subspace iteration, driven from beamfe2_b200/beam.py:
 //     Z = K^-1 (M X); A = Z^T (M X), B = Z^T (M Z); small dense generalized eigenproblem (the Jacobi kernel
 //     of bfe2.cu); X <- Z Q.  The tall-skinny contractions Z^T Y ([q x n][n x q]) and Z Q ([n x q][q x q])
@@ -52,9 +54,16 @@ struct bfe2_beam {
     void *Kd, *Kl, *Md, *Ml;    // [N][9] diagonal / sub-diagonal blocks (block (k+1,k) in Kl[k])
     void *Sinv, *G;             // [N][9] partition-local block factor
     void *Vl, *Vr;              // [N][9] spikes
-    void *RSinv, *RG, *Rl;      // [P][9] reduced system factor, Rl = block (j, j-1)
+    void *RSinv, *RG, *Rl;      // [P][9] sequentially eliminated separator system of the LAST level, Rl = block (j, j-1)
     int* d_sep;                 // [P+1] sep[-1] = -1 ... sep[P-1] = N, stored shifted by one
     int* d_part;                // [N] partition of an interior node, -1 for separator nodes
+    // second level (P2 > 0): the P - 1 separators of level 1 form a chain of their own, cut into P2 partitions
+    int P2 = 0;
+    long long N2 = 0;
+    void *Kd2 = nullptr, *Kl2 = nullptr, *Sinv2 = nullptr, *G2 = nullptr, *Vl2 = nullptr, *Vr2 = nullptr;   // [N2][9]
+    int *d_sep2 = nullptr, *d_part2 = nullptr;
+    double* u2_ws = nullptr;    // [2][3 N2 * u2_cap] right-hand sides of the separator system (high, low words)
+    long long u2_cap = 0;
     int* d_info;                // [1]
     unsigned char* d_fixed;     // [3N]
     double* lo_ws = nullptr;    // [n * lo_cap] low words of the running solution (dd only)
@@ -62,6 +71,7 @@ struct bfe2_beam {
     ~bfe2_beam() {
         if (blob) cudaFree(blob);
         if (lo_ws) cudaFree(lo_ws);
+        if (u2_ws) cudaFree(u2_ws);
     }
 };
 
@@ -144,6 +154,30 @@ __global__ void k_beam_solve_fix(long long N, const int* __restrict__ sep, const
     const int p = part_of[k];
     if (p < 0) return;                                 // separator node
     solve_fix_node<S>(k, (int)(t % U.nrhs), p, N, sep, Vl, Vr, U);
+}
+
+// ---- two-level scheme: separator system as a chain of its own (thread per separator / per (separator, rhs)) ------
+template <class S>
+__global__ void k_beam_reduced_build(int N2, const int* __restrict__ sep, const S* __restrict__ Kd,
+                                     const S* __restrict__ Kl, const S* __restrict__ Vl, const S* __restrict__ Vr,
+                                     S* Kd2, S* Kl2) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N2) return;
+    reduced_build_node<S>(j, sep, Kd, Kl, Vl, Vr, Kd2, Kl2);
+}
+
+template <class S>
+__global__ void k_beam_reduced_rhs(int N2, const int* __restrict__ sep, const S* __restrict__ Kl, MVec<S> U, MVec<S> U2) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N2 * U.nrhs) return;
+    reduced_rhs_node<S>((int)(t / U.nrhs), (int)(t % U.nrhs), sep, Kl, U, U2);
+}
+
+template <class S>
+__global__ void k_beam_reduced_scatter(int N2, const int* __restrict__ sep, MVec<S> U2, MVec<S> U) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N2 * U.nrhs) return;
+    reduced_scatter_node<S>((int)(t / U.nrhs), (int)(t % U.nrhs), sep, U2, U);
 }
 
 // ---- block tridiagonal matvec / residual: thread per (node, rhs) ---------------------------------
@@ -281,8 +315,21 @@ int beam_build(bfe2_beam* h, const double* coords, const double* props, cudaStre
                                                    (S*)h->G, h->d_info);
     k_beam_spikes<S><<<(P * 6 + 31) / 32, 32, 0, st>>>(P, h->N, h->d_sep, (const S*)h->Kl, (const S*)h->Sinv,
                                                        (const S*)h->G, (S*)h->Vl, (S*)h->Vr);
-    k_beam_reduced_factor<S><<<1, 32, 0, st>>>(P, h->d_sep, (const S*)h->Kd, (const S*)h->Kl, (const S*)h->Vl,
-                                               (const S*)h->Vr, (S*)h->RSinv, (S*)h->RG, (S*)h->Rl, h->d_info);
+    if (h->P2 == 0) {
+        k_beam_reduced_factor<S><<<1, 32, 0, st>>>(P, h->d_sep, (const S*)h->Kd, (const S*)h->Kl, (const S*)h->Vl,
+                                                   (const S*)h->Vr, (S*)h->RSinv, (S*)h->RG, (S*)h->Rl, h->d_info);
+    } else {                                           // the separator system gets the same treatment once more
+        const int N2 = (int)h->N2, P2 = h->P2;
+        k_beam_reduced_build<S><<<(N2 + 63) / 64, 64, 0, st>>>(N2, h->d_sep, (const S*)h->Kd, (const S*)h->Kl,
+                                                               (const S*)h->Vl, (const S*)h->Vr, (S*)h->Kd2, (S*)h->Kl2);
+        k_beam_factor<S><<<(P2 + 31) / 32, 32, 0, st>>>(P2, h->d_sep2, (const S*)h->Kd2, (const S*)h->Kl2,
+                                                        (S*)h->Sinv2, (S*)h->G2, h->d_info);
+        k_beam_spikes<S><<<(P2 * 6 + 31) / 32, 32, 0, st>>>(P2, h->N2, h->d_sep2, (const S*)h->Kl2, (const S*)h->Sinv2,
+                                                            (const S*)h->G2, (S*)h->Vl2, (S*)h->Vr2);
+        k_beam_reduced_factor<S><<<1, 32, 0, st>>>(P2, h->d_sep2, (const S*)h->Kd2, (const S*)h->Kl2,
+                                                   (const S*)h->Vl2, (const S*)h->Vr2, (S*)h->RSinv, (S*)h->RG,
+                                                   (S*)h->Rl, h->d_info);
+    }
     BEAM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -295,8 +342,25 @@ int beam_solve(bfe2_beam* h, int nrhs, double* U, double* Ulo, cudaStream_t st) 
     k_beam_solve_part<S><<<(unsigned)((t1 + T - 1) / T), T, 0, st>>>(h->P, h->d_sep, (const S*)h->Sinv,
                                                                      (const S*)h->G, mv);
     if (h->P > 1) {
-        k_beam_solve_reduced<S><<<(nrhs + 31) / 32, 32, 0, st>>>(h->P, h->d_sep, (const S*)h->Kl,
-                                                                 (const S*)h->RSinv, (const S*)h->RG, mv);
+        if (h->P2 == 0) {
+            k_beam_solve_reduced<S><<<(nrhs + 31) / 32, 32, 0, st>>>(h->P, h->d_sep, (const S*)h->Kl,
+                                                                     (const S*)h->RSinv, (const S*)h->RG, mv);
+        } else {
+            const int N2 = (int)h->N2, P2 = h->P2;
+            MVec<S> mv2{h->u2_ws, Ulo ? h->u2_ws + 3 * h->N2 * h->u2_cap : nullptr, nrhs};
+            const long long t2 = (long long)N2 * nrhs;
+            k_beam_reduced_rhs<S><<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(N2, h->d_sep, (const S*)h->Kl, mv, mv2);
+            const long long tp = (long long)P2 * nrhs;
+            k_beam_solve_part<S><<<(unsigned)((tp + T - 1) / T), T, 0, st>>>(P2, h->d_sep2, (const S*)h->Sinv2,
+                                                                             (const S*)h->G2, mv2);
+            if (P2 > 1) {
+                k_beam_solve_reduced<S><<<(nrhs + 31) / 32, 32, 0, st>>>(P2, h->d_sep2, (const S*)h->Kl2,
+                                                                         (const S*)h->RSinv, (const S*)h->RG, mv2);
+                k_beam_solve_fix<S><<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(h->N2, h->d_sep2, h->d_part2,
+                                                                                  (const S*)h->Vl2, (const S*)h->Vr2, mv2);
+            }
+            k_beam_reduced_scatter<S><<<(unsigned)((t2 + 127) / 128), 128, 0, st>>>(N2, h->d_sep, mv2, mv);
+        }
         const long long t3 = h->N * nrhs;
         k_beam_solve_fix<S><<<(unsigned)((t3 + 127) / 128), 128, 0, st>>>(h->N, h->d_sep, h->d_part,
                                                                           (const S*)h->Vl, (const S*)h->Vr, mv);
@@ -327,6 +391,18 @@ int beam_lo_workspace(bfe2_beam* h, int nrhs) {
     return 0;
 }
 
+// right-hand sides of the second-level chain (two-level handles only)
+int beam_u2_workspace(bfe2_beam* h, int nrhs) {
+    if (h->P2 == 0 || nrhs <= h->u2_cap) return 0;
+    BEAM_CUDA(cudaDeviceSynchronize());
+    if (h->u2_ws) cudaFree(h->u2_ws);
+    h->u2_ws = nullptr;
+    h->u2_cap = 0;
+    BEAM_CUDA(cudaMalloc(&h->u2_ws, (size_t)2 * 3 * h->N2 * nrhs * sizeof(double)));
+    h->u2_cap = nrhs;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -345,27 +421,27 @@ int bfe2_beam_create_ex(bfe2_beam** out, int64_t n_elem, const double* coords, c
     h->prec = precision;
     h->N = n_elem + 1;
     h->n = 3 * h->N;
-    // auto: ~sqrt(N) partitions -- the interiors (length N/P, thread per partition x rhs) and the separator system
+    // one level: ~sqrt(N) partitions -- the interiors (length N/P, thread per partition x rhs) and the separator system
     // (length P, eliminated sequentially) are then equally long chains; measured at n = 1e5 in double-double: P = 256
-    // 2.4 ms per solve, 1024 3.5 ms, 1562 4.9 ms, 4096 12 ms (profiles/r2_config4_partitions.txt)
-    int P = n_partitions > 0 ? n_partitions : (int)std::min<long long>(4096, std::max<long long>(1, (long long)sqrt((double)h->N)));
-    while (P > 1 && h->N < 3LL * P) --P;               // every partition needs at least one interior node
+    // 2.4 ms per solve, 1024 3.5 ms, 4096 12 ms (profiles/r2_config4_partitions.txt).  Two levels (automatic from
+    // N = 4096 on): the separator system is cut again, three chains of ~cbrt(N) steps each.
+    int P = 1, P2 = 0;
+    choose_levels(h->N, n_partitions, P, P2);
     h->P = P;
-    std::vector<int> sep(P + 1);
-    sep[0] = -1;
-    sep[P] = (int)h->N;
-    for (int j = 1; j < P; ++j) sep[j] = (int)((long long)j * h->N / P);
-    std::vector<int> part_of(h->N, 0);
-    for (int p = 0; p < P; ++p) {
-        for (int k = sep[p] + 1; k < sep[p + 1]; ++k) part_of[k] = p;
-        if (p + 1 < P) part_of[sep[p + 1]] = -1;
-    }
+    h->P2 = P2;
+    h->N2 = P2 > 0 ? P - 1 : 0;
+    std::vector<int> sep, part_of, sep2, part2;
+    cut_chain(h->N, P, sep, part_of);
+    if (P2 > 0) cut_chain(h->N2, P2, sep2, part2);
+    const int PL = P2 > 0 ? P2 : P;                    // partitions of the last level: size of the sequential system
     const size_t es = precision == BFE2_BEAM_DD ? sizeof(dd) : sizeof(double);
     const size_t nb = (size_t)h->N * 9 * es;
-    const size_t pb = (size_t)(P + 1) * 9 * es;
+    const size_t pb = (size_t)(PL + 1) * 9 * es;
+    const size_t nb2 = (size_t)(h->N2 + 1) * 9 * es;
     auto r64 = [](size_t b) { return (b + 63) & ~size_t(63); };
     const size_t total = 8 * r64(nb) + 3 * r64(pb) + r64((size_t)(P + 1) * sizeof(int)) +
-                         r64((size_t)h->N * sizeof(int)) + r64(sizeof(int)) + r64((size_t)h->n) + 256;
+                         r64((size_t)h->N * sizeof(int)) + r64(sizeof(int)) + r64((size_t)h->n) + 256 +
+                         (P2 > 0 ? 6 * r64(nb2) + r64((size_t)(P2 + 1) * sizeof(int)) + r64((size_t)h->N2 * sizeof(int)) : 0);
     if (cudaMalloc(&h->blob, total) != cudaSuccess) {
         h->blob = nullptr;
         return bfe2_fail(-100, "cudaMalloc of %zu bytes failed", total);
@@ -379,6 +455,13 @@ int bfe2_beam_create_ex(bfe2_beam** out, int64_t n_elem, const double* coords, c
     h->d_part = (int*)take(h->N * sizeof(int));
     h->d_info = (int*)take(sizeof(int));
     h->d_fixed = (unsigned char*)take(h->n);
+    if (P2 > 0) {
+        h->Kd2 = take(nb2); h->Kl2 = take(nb2); h->Sinv2 = take(nb2); h->G2 = take(nb2); h->Vl2 = take(nb2); h->Vr2 = take(nb2);
+        h->d_sep2 = (int*)take((P2 + 1) * sizeof(int));
+        h->d_part2 = (int*)take(h->N2 * sizeof(int));
+        BEAM_CUDA(cudaMemcpyAsync(h->d_sep2, sep2.data(), (P2 + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        BEAM_CUDA(cudaMemcpyAsync(h->d_part2, part2.data(), h->N2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
     BEAM_CUDA(cudaMemcpyAsync(h->d_sep, sep.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     BEAM_CUDA(cudaMemcpyAsync(h->d_part, part_of.data(), h->N * sizeof(int), cudaMemcpyHostToDevice, st));
     BEAM_CUDA(cudaMemcpyAsync(h->d_fixed, fixed_mask, h->n, cudaMemcpyHostToDevice, st));
@@ -421,6 +504,7 @@ int bfe2_beam_solve_dd(bfe2_beam* h, int32_t nrhs, const double* F, const double
         lo = h->lo_ws;
     }
     if (h->prec != BFE2_BEAM_DD) lo = nullptr;
+    if (const int rc = beam_u2_workspace(h, nrhs)) return rc;
     const long long count = h->n * (long long)nrhs;
     k_beam_load_rhs<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, F, F_lo, U, lo);
     const int rc = h->prec == BFE2_BEAM_DD ? beam_solve<dd>(h, nrhs, U, lo, st) : beam_solve<double>(h, nrhs, U, nullptr, st);

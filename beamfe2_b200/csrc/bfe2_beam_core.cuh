@@ -8,6 +8,9 @@
 // K_ii = 1, M_ii = 0 and zero couplings (DOF numbering stays the reference's, Structure.py:379-393).
 #pragma once
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
 #include "bfe2_dd.cuh"
 
 namespace bfe2 {
@@ -374,6 +377,76 @@ BFE2_HD int reduced_factor(int P, const int* sep, const S* Kd, const S* Kl, cons
     return 0;
 }
 
+// ---- two-level scheme: the separator system of level 1 is itself a block tridiagonal chain (node j = separator
+//      sep[j + 1]); instead of eliminating it sequentially (P - 1 steps) it is handed to the same partitioned
+//      machinery once more.  Kd2[j] = Schur diagonal S_j, Kl2[j] = block (j + 1, j).  Thread per separator.
+template <class S>
+BFE2_HD void reduced_build_node(int j, const int* sep, const S* Kd, const S* Kl, const S* Vl, const S* Vr, S* Kd2,
+                                S* Kl2) {
+    typedef sc<S> T;
+    S Sk[9], L1[9], L2[9], A[9], B[9];
+    const S half = T::make(0.5);
+    const long long s = sep[j + 1];
+    m3_load(Sk, Kd + 9 * s);
+    m3_load(L1, Kl + 9 * (s - 1));                     // block (s, s-1)
+    m3_load(L2, Kl + 9 * s);                           // block (s+1, s)
+    m3_load(A, Vr + 9 * (s - 1));
+    m3_load(B, Vl + 9 * (s + 1));
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            DotAcc<S> acc;
+            acc.init(Sk[3 * a + b]);
+            for (int i = 0; i < 3; ++i) acc.sub(L1[3 * a + i], A[3 * i + b]);      // L[s-1] Vr[s-1]
+            for (int i = 0; i < 3; ++i) acc.sub(L2[3 * i + a], B[3 * i + b]);      // L[s]^T Vl[s+1]
+            Sk[3 * a + b] = acc.get();
+        }
+    Sk[1] = Sk[3] = half * (Sk[1] + Sk[3]);            // the two spike routes agree only to rounding
+    Sk[2] = Sk[6] = half * (Sk[2] + Sk[6]);
+    Sk[5] = Sk[7] = half * (Sk[5] + Sk[7]);
+    m3_store(Kd2 + 9 * (long long)j, Sk);
+    if (j > 0) {                                       // block (j, j-1) = -L[s-1] Vl[s-1]
+        m3_load(A, Vl + 9 * (s - 1));
+        S R[9];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                DotAcc<S> acc;
+                acc.init(T::make(0.0));
+                for (int i = 0; i < 3; ++i) acc.sub(L1[3 * a + i], A[3 * i + b]);
+                R[3 * a + b] = acc.get();
+            }
+        m3_store(Kl2 + 9 * (long long)(j - 1), R);
+    }
+}
+
+// right-hand side of the separator system: g_j = y_s - L[s-1] y[s-1] - L[s]^T y[s+1] (y = stage-1 result in U) -> U2
+template <class S>
+BFE2_HD void reduced_rhs_node(int j, int r, const int* sep, const S* Kl, const MVec<S>& U, const MVec<S>& U2) {
+    const long long nrhs = U.nrhs, ns = 3 * nrhs;
+    const long long s = sep[j + 1];
+    S A[9], B[9], ym[3], yp[3];
+    m3_load(A, Kl + 9 * (s - 1));
+    m3_load(B, Kl + 9 * s);
+    for (int d = 0; d < 3; ++d) {
+        ym[d] = U.get((s - 1) * ns + r + d * nrhs);
+        yp[d] = U.get((s + 1) * ns + r + d * nrhs);
+    }
+    for (int d = 0; d < 3; ++d) {
+        DotAcc<S> acc;
+        acc.init(U.get(s * ns + r + d * nrhs));
+        for (int i = 0; i < 3; ++i) acc.sub(A[3 * d + i], ym[i]);
+        for (int i = 0; i < 3; ++i) acc.sub(B[3 * i + d], yp[i]);
+        U2.put((long long)j * ns + r + d * nrhs, acc.get());
+    }
+}
+
+// separator values back into the full vector
+template <class S>
+BFE2_HD void reduced_scatter_node(int j, int r, const int* sep, const MVec<S>& U2, const MVec<S>& U) {
+    const long long nrhs = U.nrhs, ns = 3 * nrhs;
+    const long long s = sep[j + 1];
+    for (int d = 0; d < 3; ++d) U.put(s * ns + r + d * nrhs, U2.get((long long)j * ns + r + d * nrhs));
+}
+
 // solve, stage 2 (one right-hand side r): reduced rhs, sequential separator solve, x_s into U
 template <class S>
 BFE2_HD void solve_reduced_rhs(int P, int r, const int* sep, const S* Kl, const S* RSinv, const S* RG,
@@ -504,6 +577,35 @@ BFE2_HD void matvec_node(long long k, int r, long long N, const S* D, const S* L
         const long long o = k * ns + r + d * nrhs;
         Y[o] = F ? T::hi(T::make(F[o]) - y[d]) : T::hi(y[d]);
     }
+}
+
+// ---- host side: how a chain of N block rows is cut (shared by bfe2_beam.cu and tools/beam_host_check.cu) ------------
+// P partitions separated by single nodes: sep[0] = -1, sep[P] = N, part[k] = partition of an interior node, -1 for a
+// separator.
+inline void cut_chain(long long N, int P, std::vector<int>& sep, std::vector<int>& part) {
+    sep.assign(P + 1, 0);
+    sep[0] = -1;
+    sep[P] = (int)N;
+    for (int j = 1; j < P; ++j) sep[j] = (int)((long long)j * N / P);
+    part.assign(N, 0);
+    for (int p = 0; p < P; ++p) {
+        for (int k = sep[p] + 1; k < sep[p + 1]; ++k) part[k] = p;
+        if (p + 1 < P) part[sep[p + 1]] = -1;
+    }
+}
+// request > 0: ONE level with that many partitions; request < 0: TWO levels with -request partitions on the first;
+// request = 0: automatic -- one level with ~sqrt(N) partitions for short chains, two levels from N = 4096 on with
+// interiors, second-level interiors and the last sequential system all ~cbrt(N) long (the three chains a solve walks).
+// P2 = 0 means one level.  Every partition keeps at least one interior node.
+inline void choose_levels(long long N, int request, int& P1, int& P2) {
+    auto fit = [](long long n, long long p) { while (p > 1 && n < 3 * p) --p; return (int)std::max<long long>(1, p); };
+    const bool two = request < 0 || (request == 0 && N >= 4096);
+    if (request > 0) P1 = fit(N, request);
+    else if (request < 0) P1 = fit(N, -(long long)request);
+    else if (!two) P1 = fit(N, std::min<long long>(4096, (long long)std::sqrt((double)N)));
+    else P1 = fit(N, (long long)(N / std::max(4.0, std::cbrt((double)N))));
+    P2 = 0;
+    if (two && P1 - 1 >= 6) P2 = fit(P1 - 1, (long long)std::sqrt((double)(P1 - 1)));
 }
 
 }  // namespace chain

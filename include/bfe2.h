@@ -202,6 +202,12 @@ int bfe2_sym_eig_dense(bfe2_plan* dense_plan, int64_t Bt, const double* A, const
  *      Precision: cond(K) ~ 16 n^4 (1.6e21 at n = 1e5), so the element matrices, the factorisation and the
  *      substitutions run in double-double (BFE2_BEAM_DD, the default of bfe2_beam_create; the inputs are exact
  *      FP64 numbers, eps * cond stays ~2e-11); BFE2_BEAM_FP64 instantiates the same kernels in plain FP64.
+ *      Partitioning (n_partitions): the chain is cut into partitions separated by single nodes, factorised
+ *      independently; the separator system is again a block tridiagonal chain.  > 0: ONE level with that many
+ *      partitions, the separator system eliminated sequentially.  < 0: TWO levels with -n_partitions partitions on the
+ *      first -- the separator system is cut the same way once more (~sqrt of it), only ITS separator system is
+ *      sequential.  0: automatic -- one level of ~sqrt(N) partitions below 4096 nodes, two levels above with the three
+ *      sequential chains of a solve (interiors, second-level interiors, last system) ~cbrt(N) steps each.
  *      A handle owns scratch for the low words of a running solve: use it from ONE stream at a time. ---- */
 typedef struct bfe2_beam bfe2_beam;
 #define BFE2_BEAM_FP64 0

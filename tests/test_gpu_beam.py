@@ -25,7 +25,8 @@ def make(n_elem, length=1000.0, n_partitions=0, precision='dd'):
     return pk, beam
 
 
-@pytest.mark.parametrize('n_elem,parts', [(3, 0), (10, 1), (10, 3), (257, 0), (257, 5), (1000, 0), (1000, 17), (4096, 64)])
+@pytest.mark.parametrize('n_elem,parts', [(3, 0), (10, 1), (10, 3), (257, 0), (257, 5), (1000, 0), (1000, 17), (4096, 64),
+                                          (30, -8), (257, -40), (1000, -200), (4096, 0), (4500, -1400)])   # < 0, and 0 from 4096 nodes on: two levels
 def test_static_fp64_kernels_vs_banded_cholesky(n_elem, parts):
     """The plain-FP64 instantiation of the chain kernels: as accurate as scipy's banded Cholesky, i.e. within the
     conditioning of the FP64-assembled matrix (kept for comparison; the default is double-double, below)."""
@@ -44,7 +45,7 @@ def test_static_fp64_kernels_vs_banded_cholesky(n_elem, parts):
 
 
 @pytest.mark.parametrize('n_elem,parts', [(3, 0), (10, 3), (257, 5), (1000, 17), (4096, 64), (10000, 0), (100000, 0),
-                                          (100000, 500)])
+                                          (100000, 500), (257, -40), (10000, 100), (100000, -4000)])
 def test_static_double_double_vs_closed_form_and_scipy(n_elem, parts):
     """SURVEY 7.3-2 at the sizes BASELINE.json names (config 4: n = 1e5): (i) scaled residual no worse than
     scipy.linalg.solveh_banded's, (ii) error against the closed form PL^3/3EI, PL^2/2EI (nodal values of Hermitian

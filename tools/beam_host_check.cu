@@ -16,29 +16,37 @@ using namespace bfe2::chain;
 
 template <class S> struct HostBeam {
     long long N;
-    int P;
-    std::vector<int> sep, part;
+    int P, P2 = 0;                                     // P2 > 0: the separator system is a second-level chain
+    std::vector<int> sep, part, sep2, part2;
     std::vector<S> Kd, Kl, Md, Ml, Sinv, G, Vl, Vr, RSinv, RG, Rl;
+    std::vector<S> Kd2, Kl2, Sinv2, G2, Vl2, Vr2;      // level 2: N2 = P - 1 block rows
     std::vector<unsigned char> fixed;
 };
+
+// partition factor + spikes + sequential separator system of one level
+template <class S>
+static int factor_level(long long N, int P, const std::vector<int>& sep, const S* Kd, const S* Kl, S* Sinv, S* G, S* Vl,
+                        S* Vr, S* RSinv, S* RG, S* Rl, bool reduced) {
+    int bad = 0;
+#pragma omp parallel for
+    for (int p = 0; p < P; ++p) {
+        const int b = factor_partition<S>(sep[p] + 1, sep[p + 1] - 1, Kd, Kl, Sinv, G);
+        if (b) bad = b;
+    }
+#pragma omp parallel for
+    for (int t = 0; t < 6 * P; ++t) spike_column<S>(t / 6, t % 6, N, sep.data(), Kl, Sinv, G, Vl, Vr);
+    if (!bad && reduced) bad = reduced_factor<S>(P, sep.data(), Kd, Kl, Vl, Vr, RSinv, RG, Rl);
+    return bad;
+}
 
 template <class S> static HostBeam<S>* create(long long n_elem, const double* coords, const double* props,
                                               const unsigned char* fixed, int P, int* info) {
     auto* h = new HostBeam<S>();
     h->N = n_elem + 1;
     const long long N = h->N;
-    if (P <= 0) P = (int)std::min<long long>(4096, std::max<long long>(1, (long long)sqrt((double)N)));
-    while (P > 1 && N < 3LL * P) --P;
-    h->P = P;
-    h->sep.resize(P + 1);
-    h->sep[0] = -1;
-    h->sep[P] = (int)N;
-    for (int j = 1; j < P; ++j) h->sep[j] = (int)((long long)j * N / P);
-    h->part.assign(N, 0);
-    for (int p = 0; p < P; ++p) {
-        for (int k = h->sep[p] + 1; k < h->sep[p + 1]; ++k) h->part[k] = p;
-        if (p + 1 < P) h->part[h->sep[p + 1]] = -1;
-    }
+    choose_levels(N, P, h->P, h->P2);
+    P = h->P;
+    cut_chain(N, P, h->sep, h->part);
     h->fixed.assign(fixed, fixed + 3 * N);
     for (auto* v : {&h->Kd, &h->Kl, &h->Md, &h->Ml, &h->Sinv, &h->G, &h->Vl, &h->Vr}) v->resize(9 * N);
     for (auto* v : {&h->RSinv, &h->RG, &h->Rl}) v->resize(9 * (P + 1));
@@ -47,20 +55,21 @@ template <class S> static HostBeam<S>* create(long long n_elem, const double* co
         assemble_node<S>(k, N, coords, props, h->fixed.data(), false, h->Kd.data(), h->Kl.data());
         assemble_node<S>(k, N, coords, props, h->fixed.data(), true, h->Md.data(), h->Ml.data());
     }
-    int bad = 0;
+    const bool two = h->P2 > 0;
+    int bad = factor_level<S>(N, P, h->sep, h->Kd.data(), h->Kl.data(), h->Sinv.data(), h->G.data(), h->Vl.data(),
+                              h->Vr.data(), h->RSinv.data(), h->RG.data(), h->Rl.data(), !two);
+    if (!bad && two) {
+        const long long N2 = P - 1;
+        cut_chain(N2, h->P2, h->sep2, h->part2);
+        for (auto* v : {&h->Kd2, &h->Kl2, &h->Sinv2, &h->G2, &h->Vl2, &h->Vr2}) v->assign(9 * N2, S{});
+        for (auto* v : {&h->RSinv, &h->RG, &h->Rl}) v->assign(9 * (h->P2 + 1), S{});
 #pragma omp parallel for
-    for (int p = 0; p < P; ++p) {
-        const int b = factor_partition<S>(h->sep[p] + 1, h->sep[p + 1] - 1, h->Kd.data(), h->Kl.data(), h->Sinv.data(),
-                                          h->G.data());
-        if (b) bad = b;
+        for (int j = 0; j < (int)N2; ++j)
+            reduced_build_node<S>(j, h->sep.data(), h->Kd.data(), h->Kl.data(), h->Vl.data(), h->Vr.data(), h->Kd2.data(),
+                                  h->Kl2.data());
+        bad = factor_level<S>(N2, h->P2, h->sep2, h->Kd2.data(), h->Kl2.data(), h->Sinv2.data(), h->G2.data(),
+                              h->Vl2.data(), h->Vr2.data(), h->RSinv.data(), h->RG.data(), h->Rl.data(), true);
     }
-#pragma omp parallel for
-    for (int t = 0; t < 6 * P; ++t)
-        spike_column<S>(t / 6, t % 6, N, h->sep.data(), h->Kl.data(), h->Sinv.data(), h->G.data(), h->Vl.data(),
-                        h->Vr.data());
-    if (!bad)
-        bad = reduced_factor<S>(P, h->sep.data(), h->Kd.data(), h->Kl.data(), h->Vl.data(), h->Vr.data(),
-                                h->RSinv.data(), h->RG.data(), h->Rl.data());
     *info = bad;
     return h;
 }
@@ -74,10 +83,39 @@ template <class S> static void solve(HostBeam<S>* h, int nrhs, const double* F, 
     for (int p = 0; p < P; ++p)
         for (int r = 0; r < nrhs; ++r)
             part_solve_inplace<S>(mv, r, 3LL * nrhs, nrhs, h->sep[p] + 1, h->sep[p + 1] - 1, h->Sinv.data(), h->G.data());
-    if (P > 1) {
+    if (P > 1 && h->P2 == 0) {
 #pragma omp parallel for
         for (int r = 0; r < nrhs; ++r)
             solve_reduced_rhs<S>(P, r, h->sep.data(), h->Kl.data(), h->RSinv.data(), h->RG.data(), mv);
+    }
+    if (h->P2 > 0) {                                   // the separator system through the second level
+        const long long N2 = P - 1;
+        std::vector<double> u2(3 * N2 * nrhs), u2lo(3 * N2 * nrhs, 0.0);
+        MVec<S> mv2{u2.data(), Ulo ? u2lo.data() : nullptr, nrhs};
+#pragma omp parallel for collapse(2)
+        for (int j = 0; j < (int)N2; ++j)
+            for (int r = 0; r < nrhs; ++r) reduced_rhs_node<S>(j, r, h->sep.data(), h->Kl.data(), mv, mv2);
+#pragma omp parallel for collapse(2)
+        for (int p = 0; p < h->P2; ++p)
+            for (int r = 0; r < nrhs; ++r)
+                part_solve_inplace<S>(mv2, r, 3LL * nrhs, nrhs, h->sep2[p] + 1, h->sep2[p + 1] - 1, h->Sinv2.data(),
+                                      h->G2.data());
+        if (h->P2 > 1) {
+#pragma omp parallel for
+            for (int r = 0; r < nrhs; ++r)
+                solve_reduced_rhs<S>(h->P2, r, h->sep2.data(), h->Kl2.data(), h->RSinv.data(), h->RG.data(), mv2);
+#pragma omp parallel for
+            for (long long k = 0; k < N2; ++k) {
+                if (h->part2[k] < 0) continue;
+                for (int r = 0; r < nrhs; ++r)
+                    solve_fix_node<S>(k, r, h->part2[k], N2, h->sep2.data(), h->Vl2.data(), h->Vr2.data(), mv2);
+            }
+        }
+#pragma omp parallel for collapse(2)
+        for (int j = 0; j < (int)N2; ++j)
+            for (int r = 0; r < nrhs; ++r) reduced_scatter_node<S>(j, r, h->sep.data(), mv2, mv);
+    }
+    if (P > 1) {
 #pragma omp parallel for
         for (long long k = 0; k < h->N; ++k) {
             if (h->part[k] < 0) continue;
