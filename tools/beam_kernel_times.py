@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""Per-kernel device times of one config-4 solve (n = 1e5, double-double; 1 and 64 right-hand sides) from the
+torch profiler: automatic two-level partitioning and a one-level partitioning beside it."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from beamfe2_b200 import sweep
 from beamfe2_b200.beam import LargeBeam, Q
 from torch.profiler import profile, ProfilerActivity
