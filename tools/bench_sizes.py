@@ -25,7 +25,11 @@ def run(nn, B):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print('n_free %3d  B %d  %.2f ms  %.0f structures/s  sweeps %.2f  info %d' % (plan.n_free, B, ms, B / ms * 1e3, out['sweeps'].double().mean().item(), int(out['info'].abs().sum())))
-for nn, B in ((11, 100000), (20, 100000), (21, 50000), (22, 50000), (23, 20000), (25, 20000), (27, 20000), (31, 20000), (34, 10000), (39, 10000)):
+SIZES = ((11, 100000), (20, 100000), (21, 50000), (22, 50000), (23, 20000), (25, 20000), (27, 20000), (31, 20000), (34, 10000), (39, 10000))
+if len(sys.argv) > 2:                                   # python tools/bench_sizes.py jacobi 23,25  -> only these node counts
+    want = {int(v) for v in sys.argv[2].split(',')}
+    SIZES = tuple((nn, B) for nn, B in SIZES if nn in want)
+for nn, B in SIZES:
     if ENGINE == 'two_ended' and 3 * (nn - 1) > 64:
         continue
     run(nn, B)
