@@ -229,3 +229,36 @@ def test_modal_subspace_iteration(n_elem):
     G = (Phi @ MPhi).cpu().numpy()
     assert np.abs(G - np.eye(12)).max() < 1e-9
     assert util.mode_err(Phi.cpu().numpy()[:3], ps[:3]).max() < 1e-5
+
+
+@pytest.mark.parametrize('parts', [0, 40, -120, -900])
+def test_general_chain_with_interior_supports(parts):
+    """Not a cantilever: a bent chain of 3000 beams with varying sections, rollers / pins / a clamp at interior nodes
+    (some of them on separator nodes of the partitioning) and four load vectors -- a well-conditioned problem (many
+    supports): the double-double path agrees with scipy's sparse LU to 1e-10 (the FP64 comparator's own error; every
+    partitioning lands on the same 1.1e-11) and leaves a scaled residual below 1e-14, on one and on two levels."""
+    import scipy.sparse.linalg as spl
+    rng = np.random.default_rng(31)
+    nE = 3000
+    ang = np.cumsum(rng.uniform(-0.02, 0.02, nE))
+    step = rng.uniform(80.0, 120.0, nE)
+    xy = np.zeros((nE + 1, 2))
+    xy[1:, 0], xy[1:, 1] = np.cumsum(step * np.cos(ang)), np.cumsum(step * np.sin(ang))
+    props = np.stack([rng.uniform(1.9e5, 2.2e5, nE), rng.uniform(2e3, 2e4, nE), rng.uniform(1e6, 1e8, nE),
+                      rng.uniform(7e-9, 8.5e-9, nE)], axis=1)
+    fixed = [0, 1, 2]
+    for node in range(25, nE, 25):                                   # a support every 25 nodes
+        kind = node // 25 % 3
+        fixed += [3 * node + 1] if kind == 0 else ([3 * node, 3 * node + 1] if kind == 1 else [3 * node, 3 * node + 1, 3 * node + 2])
+    fixed += [3 * nE + 1]
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)     # noqa: E731
+    beam = LargeBeam(T(xy), T(props), fixed, n_partitions=parts)
+    K, M, keep = bo.chain_banded(xy, props, fixed)
+    F = np.zeros((3 * (nE + 1), 4))
+    F[keep] = rng.uniform(-1e3, 1e3, (len(keep), 4))
+    U = beam.solve(T(F)).cpu().numpy()
+    assert (U[np.asarray(fixed)] == 0).all()
+    ref = spl.splu(K.tocsc()).solve(F[keep])
+    assert util.relmax(U[keep], ref) < 1e-10
+    KU = beam.matvec(T(U)).cpu().numpy()
+    assert np.abs(KU[keep] - F[keep]).max() / (abs(K).max() * np.abs(U).max()) < 1e-14      # residual of the FP64-rounded U
